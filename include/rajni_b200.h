@@ -1,0 +1,114 @@
+/*
+ * rajni_b200.h — C ABI of the B200-native RAJNI token-pruning forward path.
+ *
+ * This is the drop-in boundary: everything the reference computes inside
+ * RAJNIViTWrapper.forward (rajni/wrapper/model.py:30-69), RAJNIAttention.forward
+ * (rajni/wrapper/attention.py:17-60) and compute_importance
+ * (rajni/wrapper/importance.py:5-34) is reachable through these entry points.
+ * The reference itself has no native layer (it is eager PyTorch); a maintainer
+ * binds this library with ctypes as shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - activations and weights are bf16, row-major; bias / LayerNorm affine /
+ *     scores are fp32; indices are int32;
+ *   - `stream` is a cudaStream_t passed as void*; no call synchronises, allocates
+ *     device memory, or touches the host beyond launching kernels;
+ *   - return 0 on success, a negative RAJNI_E* code otherwise; the message is
+ *     available from rajni_last_error() (thread-local);
+ *   - sm_100a only. There is no CPU path and no fallback.
+ */
+#ifndef RAJNI_B200_H
+#define RAJNI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAJNI_ABI_VERSION 1
+
+enum {
+    RAJNI_OK = 0,
+    RAJNI_EINVAL = -1,   /* bad shape / null pointer / unsupported size          */
+    RAJNI_ECUDA = -2,    /* a CUDA runtime or driver call failed                 */
+    RAJNI_EARCH = -3,    /* current device is not compute capability 10.x        */
+    RAJNI_ERANGE = -4    /* keep > N-1: the reference's topk raises here         */
+};
+
+/* epilogue flags for rajni_gemm_bf16 */
+enum {
+    RAJNI_EPI_BIAS = 1,       /* + bias[n]                                       */
+    RAJNI_EPI_GELU = 2,       /* exact erf GELU (timm nn.GELU) after bias        */
+    RAJNI_EPI_RESIDUAL = 4,   /* + residual[res_row(m), n] after activation      */
+    RAJNI_EPI_OUT_F32 = 8     /* store fp32 instead of bf16                      */
+};
+
+int rajni_abi_version(void);
+const char* rajni_last_error(void);
+/* 0 if the current CUDA device can run this library (cc 10.x), else RAJNI_EARCH. */
+int rajni_device_check(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t rajni_launch_count(void);
+
+/* ---- a1: compute_importance (rajni/wrapper/importance.py:5-34) ------------------
+ * qkv [B,N,3C] bf16 with the last dim laid out (3,H,D); scores [B,N] fp32.
+ * bf16 tiles in, fp32 arithmetic. D must be 64. */
+int rajni_importance(const void* qkv, int B, int N, int C, int H, float eps,
+                     float* scores, void* stream);
+
+/* ---- a2: token selection (rajni/wrapper/attention.py:31-39) and score carry (:58)
+ * Top-`keep` of scores[:,1:] -> keep_idx [B,keep+1] int32, strictly ascending,
+ * keep_idx[:,0]==0. Tie rule: greater score first, then lower index.
+ * next_scores [B,keep+1] = scores[keep_idx]. row_map [B*(keep+1)] = b*N+keep_idx
+ * (global row of each kept token; nullable). keep > N-1 -> RAJNI_ERANGE. */
+int rajni_select(const float* scores, int B, int N, int keep,
+                 int32_t* keep_idx, float* next_scores, int32_t* row_map, void* stream);
+
+/* ---- a1+a2 fused: one pass over the K and V planes, then in-CTA select.
+ * scores may be NULL when the caller does not need the full score vector. */
+int rajni_score_select(const void* qkv, int B, int N, int C, int H, int keep, float eps,
+                       float* scores, int32_t* keep_idx, float* next_scores,
+                       int32_t* row_map, void* stream);
+
+/* ---- a3 / a9: row gather-compaction (attention.py:42-43, model.py:55-56)
+ * dst[r, :] = src[row_map[r], :], rows of `row_elems` bf16 (multiple of 8). */
+int rajni_gather_rows(const void* src, const int32_t* row_map, void* dst,
+                      int rows_out, int row_elems, void* stream);
+
+/* ---- LayerNorm over the last dim (model.py:51,59,65), bf16 -> bf16, fp32 math.
+ * Row r is read at x + r*in_row_stride elements (lets the final norm touch CLS
+ * rows only) and written densely at y + r*C. C multiple of 8, C <= 4096. */
+int rajni_layernorm(const void* x, long long in_row_stride, const float* gamma,
+                    const float* beta, float eps, void* y, int rows, int C, void* stream);
+
+/* ---- dense contractions (attention.py:22,55; timm Mlp fc1/fc2; patch_embed; head)
+ * D[orow(m), n] = epi( sum_k A[m,k] * W[n,k] ), A [M,K] bf16, W [N,K] bf16
+ * (nn.Linear layout), fp32 accumulation in TMEM (tcgen05.mma, TMA-fed).
+ *   orow(m) = out_row_map ? out_row_map[m] : m
+ *   res row = res_row_map ? res_row_map[m] : m      (gathered residual, model.py:55-58)
+ * K multiple of 8; ldd/ldres are row strides in elements (multiples of 8). */
+int rajni_gemm_bf16(const void* A, const void* W, const float* bias, void* D,
+                    int M, int N, int K, int flags,
+                    const void* residual, long long ldres, const int32_t* res_row_map,
+                    long long ldd, const int32_t* out_row_map, void* stream);
+
+/* ---- a4: multi-head attention over kept tokens (attention.py:45-54)
+ * qkv [B,N_src,3C] bf16; when row_map != NULL token j of image b is read from
+ * global row row_map[b*Np+j] (gather fused into the loads), else N_src == Np.
+ * out [B,Np,C] bf16 = softmax(q k^T * scale) v, heads concatenated. D must be 64. */
+int rajni_attention_fwd(const void* qkv, const int32_t* row_map, void* out,
+                        int B, int N_src, int Np, int C, int H, float scale, void* stream);
+
+/* ---- a8: patch-embed front end (model.py:31-37)
+ * im2col: images [B,3,S,S] (fp32 if images_f32 else bf16) -> cols [B*P, 3*p*p] bf16
+ * in Conv2d weight order (c, ky, kx). Also writes the CLS rows
+ * x[b,0,:] = cls_pos0[:] (= cls_token + pos_embed[0], precomputed) into x [B,1+P,C]. */
+int rajni_patch_im2col(const void* images, int images_f32, int B, int S, int patch,
+                       void* cols, const void* cls_pos0, void* x, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAJNI_B200_H */

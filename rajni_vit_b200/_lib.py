@@ -1,0 +1,73 @@
+"""ctypes binding of librajni_b200.so (the C ABI in include/rajni_b200.h).
+
+There is no CPU path and no fallback: if the library is missing, cannot be
+loaded, or the device is not sm_100, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "librajni_b200.so")
+
+RAJNI_OK, RAJNI_EINVAL, RAJNI_ECUDA, RAJNI_EARCH, RAJNI_ERANGE = 0, -1, -2, -3, -4
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32 = 1, 2, 4, 8
+ABI_VERSION = 1
+
+# symbol -> (restype, argtypes); mirrors include/rajni_b200.h one to one
+SIGNATURES = {
+    "rajni_abi_version": (c_int, []),
+    "rajni_last_error": (c_char_p, []),
+    "rajni_device_check": (c_int, []),
+    "rajni_launch_count": (c_uint64, []),
+    "rajni_importance": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "rajni_select": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rajni_score_select": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rajni_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "rajni_layernorm": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p]),
+    "rajni_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p]),
+    "rajni_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "rajni_patch_im2col": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+class RajniError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(message)
+        self.code = code
+
+
+def load() -> ctypes.CDLL:
+    """Load the library (once). Raises if it has not been built — there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m rajni_vit_b200.csrc.build` "
+            "(or __graft_entry__.build()). rajni_vit_b200 has no CPU or eager fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    if lib.rajni_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"librajni_b200.so ABI {lib.rajni_abi_version()} != expected {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != RAJNI_OK:
+        msg = load().rajni_last_error().decode("utf-8", "replace")
+        raise RajniError(rc, msg)
+
+
+def launch_count() -> int:
+    return int(load().rajni_launch_count())

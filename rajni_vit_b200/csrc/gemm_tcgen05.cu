@@ -1,0 +1,359 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> smem ring -> tcgen05.mma -> TMEM
+// -> fused epilogue (bias, exact-erf GELU, gathered residual, row-remapped store).
+//
+//   D[orow(m), n] = epi( sum_k A[m,k] * W[n,k] )         A [M,K], W [N,K] (nn.Linear layout)
+//
+// Serves every dense contraction on the path: qkv (attention.py:22), proj (attention.py:55)
+// with the kept-token residual gather folded into the epilogue (model.py:55-58), fc1+GELU,
+// fc2+residual (model.py:59), patch-embed as a GEMM over im2col'd patches (+pos_embed as the
+// "residual", model.py:34-37) and the classifier head (model.py:66).
+//
+// CTA = 384 threads, one CTA per SM, tiles 128 x BN x 64:
+//   warp 0   : TMA producer (one lane)         warp 1 : tcgen05.mma issuer (one lane)
+//   warp 2   : TMEM allocator                  warp 3 : idle
+//   warps 4-11: epilogue; warp w reads TMEM lanes 32*(w%4).. and column half (w-4)/4
+// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace rajni {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 bf16 = one 128-byte swizzle row
+constexpr int kGemmThreads = 384;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiStageBytes = 32 * 128;   // per-warp staging: 32 rows x 32 fp32
+
+template <int BN> struct GemmCfg {
+    static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = 2 * BN;               // double-buffered accumulator
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 256 /*barriers*/ + 1024 /*align*/;
+};
+
+struct GemmParams {
+    const float* bias;
+    void* D;
+    const __nv_bfloat16* residual;
+    const int32_t* res_row_map;
+    const int32_t* out_row_map;
+    long long ldd, ldres;
+    int M, N, K, flags;
+    int tiles_m, tiles_n, k_blocks;
+};
+
+// Exact-erf GELU (timm nn.GELU) evaluated as x*Phi(x) with
+//   Phi(-a) = 0.5 * 2^(-a*P(a)),  a = min(|x|, 6),  P = degree-6 minimax fit of -log2(erfc(a/sqrt2))/a.
+// Max relative error 2.3e-5 over |x| <= 5.5 (absolute 1.5e-6), i.e. ~100x below bf16 rounding;
+// 11 FP32 instructions + one MUFU.EX2 instead of erff's ~30 (the fc1 epilogue is otherwise
+// CUDA-core bound: 768 MACs per output leave ~24 instruction slots per element).
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float a = fminf(fabsf(x), 6.0f);
+    float p = 1.339070422545774e-06f;
+    p = fmaf(p, a, -5.1697126764338464e-05f);
+    p = fmaf(p, a, 0.0008538772817701101f);
+    p = fmaf(p, a, -0.008219408802688122f);
+    p = fmaf(p, a, 0.05341951176524162f);
+    p = fmaf(p, a, 0.45892229676246643f);
+    p = fmaf(p, a, 1.1511197090148926f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a * p));
+    const float s = x * (0.5f * e);
+    return x >= 0.f ? x - s : s;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_a = smem;                                        // [stages][128][64] bf16, SW128
+    uint8_t* s_b = smem + Cfg::kStages * Cfg::kABytes;          // [stages][BN][64] bf16, SW128
+    uint8_t* s_epi = smem + Cfg::kStages * Cfg::kStageBytes;    // [8 warps][32][32] fp32
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + kEpiWarps * kEpiStageBytes);
+    uint64_t* full_bar = bars;                                  // [stages]
+    uint64_t* empty_bar = bars + Cfg::kStages;                  // [stages]
+    uint64_t* tmem_full = bars + 2 * Cfg::kStages;              // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps); }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_2d(s_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                    tma_load_2d(s_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+                const int acc = local & 1;
+                const uint32_t acc_phase = (local >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(s_a + stage * Cfg::kABytes);
+                    const uint32_t b_addr = smem_u32(s_b + stage * Cfg::kBBytes);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advancing 16 bf16 along K = +32 bytes inside the 128-byte swizzle row
+                        const uint64_t a_desc = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+                        const uint64_t b_desc = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+                        umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);                  // frees the smem slot when these MMAs finish
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);                        // accumulator ready for the epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int ew = warp - 4;
+        const int sub = warp & 3;                   // TMEM sub-partition = warp id % 4
+        const int half = ew >> 2;                   // which half of the BN columns
+        float* stg = reinterpret_cast<float*>(s_epi + ew * kEpiStageBytes);
+        const bool has_bias = (p.flags & RAJNI_EPI_BIAS) != 0;
+        const bool do_gelu = (p.flags & RAJNI_EPI_GELU) != 0;
+        const bool has_res = (p.flags & RAJNI_EPI_RESIDUAL) != 0;
+        const bool out_f32 = (p.flags & RAJNI_EPI_OUT_F32) != 0;
+        const int r_in = lane >> 3;                 // row within a group of 4 (phase 2)
+        const int c4 = lane & 7;                    // 4-column group within the 32-column chunk
+        int local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+            const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+            const int acc = local & 1;
+            const uint32_t acc_phase = (local >> 1) & 1;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row0 = m_blk * BM + sub * 32;
+            // rows this lane stores in phase 2: row0 + it*4 + r_in
+            long long orow[8], rrow[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int m = row0 + it * 4 + r_in;
+                if (m < p.M) {
+                    orow[it] = p.out_row_map ? (long long)__ldg(p.out_row_map + m) : (long long)m;
+                    rrow[it] = has_res ? (p.res_row_map ? (long long)__ldg(p.res_row_map + m) : (long long)m) : 0;
+                } else {
+                    orow[it] = -1;
+                    rrow[it] = 0;
+                }
+            }
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 64; ++ch) {
+                const int col_in_tile = half * (BN / 2) + ch * 32;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN + col_in_tile), v);
+                tmem_ld_wait();
+                // phase 1: thread = row; write 8 x 16 B with an XOR swizzle (conflict-free)
+                {
+                    uint4* rowp = reinterpret_cast<uint4*>(stg + lane * 32);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        rowp[c ^ (lane & 7)] = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                }
+                __syncwarp();
+                // phase 2: 8 lanes per row, 4 rows per instruction -> coalesced global traffic
+                const int n = n_blk * BN + col_in_tile + c4 * 4;
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_bias && n < p.N) {
+                    if (n + 4 <= p.N) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                    else {
+                        bv.x = __ldg(p.bias + n);
+                        if (n + 1 < p.N) bv.y = __ldg(p.bias + n + 1);
+                        if (n + 2 < p.N) bv.z = __ldg(p.bias + n + 2);
+                    }
+                }
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + r_in;
+                    float4 a = *reinterpret_cast<const float4*>(stg + r * 32 + ((c4 ^ (r & 7)) << 2));
+                    if (orow[it] < 0 || n >= p.N) continue;
+                    a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
+                    if (do_gelu) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+                    const bool full4 = (n + 4 <= p.N);
+                    if (has_res) {
+                        const __nv_bfloat16* rp = p.residual + rrow[it] * p.ldres + n;
+                        if (full4) {
+                            const uint2 rr = __ldg(reinterpret_cast<const uint2*>(rp));
+                            const float2 r0 = bf16x2_to_float2(rr.x), r1 = bf16x2_to_float2(rr.y);
+                            a.x += r0.x; a.y += r0.y; a.z += r1.x; a.w += r1.y;
+                        } else {
+                            a.x += __bfloat162float(rp[0]);
+                            if (n + 1 < p.N) a.y += __bfloat162float(rp[1]);
+                            if (n + 2 < p.N) a.z += __bfloat162float(rp[2]);
+                        }
+                    }
+                    if (out_f32) {
+                        float* dp = static_cast<float*>(p.D) + orow[it] * p.ldd + n;
+                        if (full4) *reinterpret_cast<float4*>(dp) = a;
+                        else {
+                            dp[0] = a.x;
+                            if (n + 1 < p.N) dp[1] = a.y;
+                            if (n + 2 < p.N) dp[2] = a.z;
+                        }
+                    } else {
+                        __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(p.D) + orow[it] * p.ldd + n;
+                        if (full4) *reinterpret_cast<uint2*>(dp) = make_uint2(float2_to_bf16x2(a.x, a.y), float2_to_bf16x2(a.z, a.w));
+                        else {
+                            dp[0] = __float2bfloat16(a.x);
+                            if (n + 1 < p.N) dp[1] = __float2bfloat16(a.y);
+                            if (n + 2 < p.N) dp[2] = __float2bfloat16(a.z);
+                        }
+                    }
+                }
+                __syncwarp();           // staging is overwritten by the next chunk
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle, zero OOB fill.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols,
+                      long long ld_elems, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    RAJNI_REQUIRE(fn != nullptr, RAJNI_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RAJNI_REQUIRE(r == CUDA_SUCCESS, RAJNI_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%d",
+                  (int)r, rows, cols, ld_elems, box_rows);
+    return 0;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BN>
+static int launch_gemm(const void* A, const void* W, GemmParams& p, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    CUtensorMap ta, tb;
+    if (int rc = make_tmap_bf16_2d(&ta, A, p.M, p.K, p.K, BM)) return rc;
+    if (int rc = make_tmap_bf16_2d(&tb, W, p.N, p.K, p.K, BN)) return rc;
+    p.tiles_m = (p.M + BM - 1) / BM;
+    p.tiles_n = (p.N + BN - 1) / BN;
+    p.k_blocks = (p.K + BK - 1) / BK;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "gemm: smem attribute (%d B): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+        attr_done = true;
+    }
+    int grid = p.tiles_m * p.tiles_n;
+    if (grid > num_sms()) grid = num_sms();
+    gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+    count_launch();
+    return check_launch("gemm_bf16");
+}
+
+}  // namespace rajni
+
+using namespace rajni;
+
+extern "C" int rajni_gemm_bf16(const void* A, const void* W, const float* bias, void* D,
+                               int M, int N, int K, int flags,
+                               const void* residual, long long ldres, const int32_t* res_row_map,
+                               long long ldd, const int32_t* out_row_map, void* stream) {
+    RAJNI_REQUIRE(A && W && D, RAJNI_EINVAL, "rajni_gemm_bf16: null pointer");
+    RAJNI_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0, RAJNI_EINVAL, "rajni_gemm_bf16: M=%d N=%d K=%d (K must be a multiple of 8)", M, N, K);
+    RAJNI_REQUIRE(!(flags & RAJNI_EPI_BIAS) || bias, RAJNI_EINVAL, "rajni_gemm_bf16: bias flag without bias");
+    RAJNI_REQUIRE(!(flags & RAJNI_EPI_RESIDUAL) || residual, RAJNI_EINVAL, "rajni_gemm_bf16: residual flag without residual");
+    RAJNI_REQUIRE(ldd >= N && ldd % 4 == 0 && (!(flags & RAJNI_EPI_RESIDUAL) || ldres % 4 == 0), RAJNI_EINVAL,
+                  "rajni_gemm_bf16: ldd=%lld ldres=%lld must be multiples of 4 and ldd >= N", ldd, ldres);
+    GemmParams p{};
+    p.bias = bias; p.D = D;
+    p.residual = static_cast<const __nv_bfloat16*>(residual);
+    p.res_row_map = res_row_map; p.out_row_map = out_row_map;
+    p.ldd = ldd; p.ldres = ldres;
+    p.M = M; p.N = N; p.K = K; p.flags = flags;
+    // tile width: minimise padded columns; the 64-wide tile runs at ~2/3 rate (shared-memory bound)
+    auto cost = [&](int bn) { long long padded = (long long)((N + bn - 1) / bn) * bn; return bn == 64 ? padded * 3 / 2 : padded; };
+    int bn = 256;
+    if (cost(128) < cost(bn)) bn = 128;
+    if (cost(64) < cost(bn)) bn = 64;
+    auto s = static_cast<cudaStream_t>(stream);
+    switch (bn) {
+        case 256: return launch_gemm<256>(A, W, p, s);
+        case 128: return launch_gemm<128>(A, W, p, s);
+        default: return launch_gemm<64>(A, W, p, s);
+    }
+}

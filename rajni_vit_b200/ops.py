@@ -1,0 +1,134 @@
+"""Tensor-level wrappers over the C ABI: torch supplies device memory and the stream,
+librajni_b200.so does the work.  Every function requires CUDA tensors on an sm_100
+device and raises otherwise (no CPU path)."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import EPI_BIAS, EPI_GELU, EPI_OUT_F32, EPI_RESIDUAL  # noqa: F401  (re-exported)
+
+_checked_devices = set()
+
+
+def _stream(t: torch.Tensor) -> int:
+    dev = t.device
+    if dev.type != "cuda":
+        raise RuntimeError("rajni_vit_b200 runs on CUDA (sm_100a) tensors only; there is no CPU path")
+    if dev.index not in _checked_devices:
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().rajni_device_check())
+        _checked_devices.add(dev.index)
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _bf16c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.bfloat16 or not t.is_contiguous():
+        raise ValueError(f"expected a contiguous bf16 tensor, got {t.dtype} contiguous={t.is_contiguous()}")
+    return t
+
+
+def importance(qkv: torch.Tensor, num_heads: int, eps: float = 1e-6) -> torch.Tensor:
+    """qkv [B,N,3C] bf16 -> scores [B,N] fp32.   importance.py:5-34"""
+    _bf16c(qkv)
+    B, N, C3 = qkv.shape
+    scores = torch.empty((B, N), device=qkv.device, dtype=torch.float32)
+    _lib.check(_lib.load().rajni_importance(qkv.data_ptr(), B, N, C3 // 3, num_heads, eps,
+                                            scores.data_ptr(), _stream(qkv)))
+    return scores
+
+
+def select(scores: torch.Tensor, keep: int, keep_idx=None, next_scores=None, row_map=None
+           ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """scores [B,N] fp32 -> (keep_idx int32 [B,keep+1], next_scores fp32, row_map int32 [B*(keep+1)])."""
+    if scores.dtype != torch.float32 or not scores.is_contiguous():
+        raise ValueError("scores must be contiguous fp32")
+    B, N = scores.shape
+    dev = scores.device
+    keep_idx = torch.empty((B, keep + 1), device=dev, dtype=torch.int32) if keep_idx is None else keep_idx
+    next_scores = torch.empty((B, keep + 1), device=dev, dtype=torch.float32) if next_scores is None else next_scores
+    row_map = torch.empty((B * (keep + 1),), device=dev, dtype=torch.int32) if row_map is None else row_map
+    _lib.check(_lib.load().rajni_select(scores.data_ptr(), B, N, keep, keep_idx.data_ptr(),
+                                        next_scores.data_ptr(), row_map.data_ptr(), _stream(scores)))
+    return keep_idx, next_scores, row_map
+
+
+def score_select(qkv: torch.Tensor, num_heads: int, keep: int, eps: float = 1e-6, want_scores: bool = False,
+                 keep_idx=None, next_scores=None, row_map=None, scores=None):
+    """Fused importance + selection on qkv [B,N,3C] bf16.
+    Returns (scores or None, keep_idx, next_scores, row_map)."""
+    _bf16c(qkv)
+    B, N, C3 = qkv.shape
+    dev = qkv.device
+    if want_scores and scores is None:
+        scores = torch.empty((B, N), device=dev, dtype=torch.float32)
+    keep_idx = torch.empty((B, keep + 1), device=dev, dtype=torch.int32) if keep_idx is None else keep_idx
+    next_scores = torch.empty((B, keep + 1), device=dev, dtype=torch.float32) if next_scores is None else next_scores
+    row_map = torch.empty((B * (keep + 1),), device=dev, dtype=torch.int32) if row_map is None else row_map
+    _lib.check(_lib.load().rajni_score_select(qkv.data_ptr(), B, N, C3 // 3, num_heads, keep, eps, _ptr(scores),
+                                              keep_idx.data_ptr(), next_scores.data_ptr(), row_map.data_ptr(),
+                                              _stream(qkv)))
+    return scores, keep_idx, next_scores, row_map
+
+
+def gather_rows(src: torch.Tensor, row_map: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """src [R,E] bf16, row_map int32 [R_out] -> out [R_out,E]."""
+    _bf16c(src)
+    rows_out, E = row_map.numel(), src.shape[-1]
+    out = torch.empty((rows_out, E), device=src.device, dtype=torch.bfloat16) if out is None else out
+    _lib.check(_lib.load().rajni_gather_rows(src.data_ptr(), row_map.data_ptr(), out.data_ptr(), rows_out, E,
+                                             _stream(src)))
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, rows: int, C: int,
+              in_row_stride: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Row LayerNorm, bf16 -> bf16; row r read at x.data_ptr + r*in_row_stride elements."""
+    out = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16) if out is None else out
+    _lib.check(_lib.load().rajni_layernorm(x.data_ptr(), C if in_row_stride is None else in_row_stride,
+                                           gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(), rows, C, _stream(x)))
+    return out
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], M: int, N: int, K: int, *,
+         gelu: bool = False, residual: Optional[torch.Tensor] = None, ldres: Optional[int] = None,
+         res_row_map: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         ldd: Optional[int] = None, out_row_map: Optional[torch.Tensor] = None, out_f32: bool = False
+         ) -> torch.Tensor:
+    """out[orow(m), n] = epi(sum_k a[m,k] w[n,k]); a [M,K] bf16, w [N,K] bf16, bias fp32 [N]."""
+    flags = (EPI_BIAS if bias is not None else 0) | (EPI_GELU if gelu else 0) | \
+            (EPI_RESIDUAL if residual is not None else 0) | (EPI_OUT_F32 if out_f32 else 0)
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    _lib.check(_lib.load().rajni_gemm_bf16(
+        a.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, flags,
+        _ptr(residual), (N if ldres is None else ldres), _ptr(res_row_map),
+        (N if ldd is None else ldd), _ptr(out_row_map), _stream(a)))
+    return out
+
+
+def attention(qkv: torch.Tensor, row_map: Optional[torch.Tensor], B: int, N_src: int, Np: int, C: int,
+              num_heads: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Attention over the Np kept tokens of each image, gather fused.  -> [B*Np, C] bf16"""
+    out = torch.empty((B * Np, C), device=qkv.device, dtype=torch.bfloat16) if out is None else out
+    _lib.check(_lib.load().rajni_attention_fwd(qkv.data_ptr(), _ptr(row_map), out.data_ptr(), B, N_src, Np, C,
+                                               num_heads, scale, _stream(qkv)))
+    return out
+
+
+def patch_im2col(images: torch.Tensor, patch: int, cols: torch.Tensor, cls_pos0: torch.Tensor,
+                 x: torch.Tensor, C: int) -> None:
+    """images [B,3,S,S] fp32|bf16 -> cols [B*P, 3*p*p] bf16; also writes the CLS rows of x."""
+    if images.dtype not in (torch.float32, torch.bfloat16) or not images.is_contiguous():
+        raise ValueError("images must be contiguous fp32 or bf16")
+    B, ch, S, S2 = images.shape
+    if ch != 3 or S != S2:
+        raise ValueError(f"images must be [B,3,S,S], got {tuple(images.shape)}")
+    _lib.check(_lib.load().rajni_patch_im2col(images.data_ptr(), int(images.dtype == torch.float32), B, S, patch,
+                                              cols.data_ptr(), cls_pos0.data_ptr(), x.data_ptr(), C, _stream(images)))

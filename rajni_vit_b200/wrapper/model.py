@@ -1,0 +1,234 @@
+"""RAJNIViTWrapper — drop-in for rajni/wrapper/model.py:6-69, running on sm_100a kernels.
+
+The class keeps the reference's constructor, attribute names (``m``, ``blocks``,
+``pruning_schedule``, ``blk.attn`` swapped for ``RAJNIAttention``, ``blk.has_pruner``),
+``forward`` and ``get_last_stats()``.  The body of ``forward`` does not call the base
+model's modules: it reads their leaf parameters and launches the kernels of
+``librajni_b200.so`` — pruned and un-pruned blocks, patch-embed and head alike.
+
+Deliberate deviations from the reference:
+  * schedule keys may be ints or digit strings (the reference silently prunes
+    nothing for the string keys that ``json.load`` produces);
+  * activations are bf16 with fp32 accumulation, scores are fp32;
+  * ties in the top-k are broken by lower index (torch.topk leaves it undefined);
+  * unsupported base models raise instead of silently diverging.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..packing import PackCache
+from .attention import RAJNIAttention, keep_count
+
+
+def _normalise_schedule(schedule: Dict) -> Dict[int, Dict]:
+    out = {}
+    for k, cfg in schedule.items():
+        if isinstance(k, str):
+            if not k.strip().lstrip("-").isdigit():
+                raise ValueError(f"pruning_schedule key {k!r} is not a block index")
+            k = int(k)
+        if "keep_ratio" not in cfg:
+            raise KeyError("keep_ratio")
+        out[int(k)] = cfg
+    return out
+
+
+def _is_identity(m) -> bool:
+    return m is None or isinstance(m, nn.Identity) or (isinstance(m, nn.Dropout) and m.p == 0.0)
+
+
+class RAJNIViTWrapper(nn.Module):
+    def __init__(self, base_model: nn.Module, pruning_schedule: Dict[int, Dict]):
+        super().__init__()
+        self.m = base_model
+        self.blocks = base_model.blocks
+        self.pruning_schedule = pruning_schedule
+        sched = _normalise_schedule(pruning_schedule)
+
+        for i, blk in enumerate(self.blocks):
+            if i in sched:
+                cfg = sched[i]
+                blk.attn = RAJNIAttention(blk.attn, keep_ratio=cfg["keep_ratio"], update=cfg.get("update", True))
+                blk.has_pruner = True
+            else:
+                blk.has_pruner = False
+
+        self._last_stats = None
+        self._last_keep_idx: List[Optional[torch.Tensor]] = []
+        self._packs = PackCache()
+        self._ws = {}
+        self._validate()
+
+    # ------------------------------------------------------------------ contract checks
+    def _validate(self):
+        m = self.m
+        proj = getattr(m.patch_embed, "proj", None)
+        if not isinstance(proj, nn.Conv2d) or proj.kernel_size != (16, 16) or proj.stride != (16, 16) or proj.in_channels != 3:
+            raise NotImplementedError("patch_embed.proj must be Conv2d(3, C, kernel=16, stride=16)")
+        if not _is_identity(getattr(m.patch_embed, "norm", None)):
+            raise NotImplementedError("patch_embed.norm is not supported")
+        for name in ("norm_pre", "fc_norm", "patch_drop"):
+            if not _is_identity(getattr(m, name, None)):
+                raise NotImplementedError(f"{name} = {type(getattr(m, name)).__name__} is not supported")
+        if getattr(m, "global_pool", "token") != "token":
+            raise NotImplementedError("only global_pool='token' (CLS) is supported")
+        if not isinstance(m.norm, nn.LayerNorm) or not isinstance(m.head, nn.Linear):
+            raise NotImplementedError("norm must be LayerNorm and head must be Linear")
+        C = proj.out_channels
+        for i, blk in enumerate(self.blocks):
+            for name in ("ls1", "ls2", "drop_path1", "drop_path2"):
+                if not _is_identity(getattr(blk, name, None)):
+                    raise NotImplementedError(f"blocks[{i}].{name} = {type(getattr(blk, name)).__name__} is not supported")
+            attn = blk.attn
+            if attn.num_heads * 64 != C:
+                raise NotImplementedError(f"blocks[{i}]: head dim must be 64 (C={C}, heads={attn.num_heads})")
+            if abs(float(attn.scale) - 0.125) > 1e-12:
+                raise NotImplementedError(f"blocks[{i}]: attention scale {attn.scale} != 64**-0.5")
+            for name in ("q_norm", "k_norm"):
+                if not _is_identity(getattr(attn, name, None)):
+                    raise NotImplementedError(f"blocks[{i}].attn.{name} is not supported")
+            act = blk.mlp.act
+            if not isinstance(act, nn.GELU) or getattr(act, "approximate", "none") != "none":
+                raise NotImplementedError(f"blocks[{i}].mlp.act must be exact (erf) nn.GELU")
+            if not _is_identity(getattr(blk.mlp, "norm", None)):
+                raise NotImplementedError(f"blocks[{i}].mlp.norm is not supported")
+            if not isinstance(blk.norm1, nn.LayerNorm) or not isinstance(blk.norm2, nn.LayerNorm):
+                raise NotImplementedError(f"blocks[{i}]: norm1/norm2 must be LayerNorm")
+
+    def _apply(self, fn, *a, **kw):
+        self._packs.clear()
+        self._ws.clear()
+        return super()._apply(fn, *a, **kw)
+
+    def get_last_stats(self):
+        return self._last_stats
+
+    # ------------------------------------------------------------------ workspace
+    def _workspace(self, B: int, S: int, dev: torch.device):
+        key = (B, S, dev)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        m = self.m
+        C = m.patch_embed.proj.out_channels
+        G = S // 16
+        P = G * G
+        N0 = P + 1
+        if m.pos_embed.shape[1] < N0:
+            raise ValueError(f"pos_embed has {m.pos_embed.shape[1]} positions, input needs {N0}")
+        hidden = max(blk.mlp.fc1.out_features for blk in self.blocks)
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        idx = torch.arange(B * P, device=dev, dtype=torch.int32)
+        ws = dict(
+            P=P, N0=N0, C=C,
+            cols=torch.empty((B * P, 768), **bf),
+            xa=torch.empty((B * N0, C), **bf), xb=torch.empty((B * N0, C), **bf),
+            xn=torch.empty((B * N0, C), **bf), qkv=torch.empty((B * N0, 3 * C), **bf),
+            att=torch.empty((B * N0, C), **bf), hid=torch.empty((B * N0, hidden), **bf),
+            cls=torch.empty((B, C), **bf),
+            embed_out_map=((idx // P) * N0 + 1 + idx % P).to(torch.int32),
+            embed_pos_map=(1 + idx % P).to(torch.int32),
+            sel={},
+        )
+        self._ws = {key: ws}        # keep one shape resident
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != x.shape[3] or x.shape[2] % 16:
+            raise ValueError(f"expected images [B,3,S,S] with S a multiple of 16, got {tuple(x.shape)}")
+        if x.device.type != "cuda":
+            raise RuntimeError("RAJNIViTWrapper (B200) runs on CUDA tensors only; there is no CPU path")
+        if self.training:
+            for blk in self.blocks:
+                for d in (blk.attn.proj_drop, getattr(blk.mlp, "drop1", None), getattr(blk.mlp, "drop2", None)):
+                    if isinstance(d, nn.Dropout) and d.p > 0:
+                        raise NotImplementedError("dropout in training mode is not supported (inference path)")
+        m = self.m
+        out_dtype = x.dtype if x.dtype.is_floating_point else torch.float32
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        x = x.contiguous()
+        B, _, S, _ = x.shape
+        ws = self._workspace(B, S, x.device)
+        P, N, C = ws["P"], ws["N0"], ws["C"]
+        pk = self._packs
+
+        # ---- patch + CLS + pos (model.py:31-37): im2col, then one GEMM whose epilogue adds
+        #      bias and pos_embed and scatters into rows 1..P of each image
+        pe_w, pe_b = pk.linear(m.patch_embed.proj)
+        pos, cls_pos0 = pk.tensors(
+            ("pos", P), (m.pos_embed, m.cls_token),
+            lambda: (m.pos_embed.detach()[0, : P + 1].to(torch.bfloat16).contiguous(),
+                     (m.cls_token.detach()[0, 0] + m.pos_embed.detach()[0, 0]).to(torch.bfloat16).contiguous()))
+        cur, nxt = ws["xa"], ws["xb"]
+        ops.patch_im2col(x, 16, ws["cols"], cls_pos0, cur, C)
+        ops.gemm(ws["cols"], pe_w, pe_b, B * P, C, 768, residual=pos, ldres=C, res_row_map=ws["embed_pos_map"],
+                 out=cur, ldd=C, out_row_map=ws["embed_out_map"])
+
+        scores = None
+        token_counts = []
+        keep_log: List[Optional[torch.Tensor]] = []
+        for i, blk in enumerate(self.blocks):
+            token_counts.append(N)                                                   # model.py:43
+            H = blk.attn.num_heads
+            g1, b1, e1 = pk.norm(blk.norm1)
+            g2, b2, e2 = pk.norm(blk.norm2)
+            qw, qb = pk.linear(blk.attn.qkv)
+            pw, pb = pk.linear(blk.attn.proj)
+            f1w, f1b = pk.linear(blk.mlp.fc1)
+            f2w, f2b = pk.linear(blk.mlp.fc2)
+            hidden = f1w.shape[0]
+            M = B * N
+            ops.layernorm(cur, g1, b1, e1, M, C, out=ws["xn"])                        # model.py:51
+            ops.gemm(ws["xn"], qw, qb, M, 3 * C, C, out=ws["qkv"])                    # attention.py:22
+            if blk.has_pruner:
+                attn: RAJNIAttention = blk.attn
+                keep = keep_count(N, attn.keep_ratio)                                 # attention.py:31-32
+                if keep > N - 1:
+                    raise RuntimeError("selected index k out of range")               # attention.py:35
+                Np = keep + 1
+                sel = ws["sel"].get(i)
+                if sel is None or sel[0].shape[1] != Np:
+                    sel = (torch.empty((B, Np), device=x.device, dtype=torch.int32),
+                           torch.empty((B, Np), device=x.device, dtype=torch.float32),
+                           torch.empty((B * Np,), device=x.device, dtype=torch.int32))
+                    ws["sel"][i] = sel
+                keep_idx, next_scores, row_map = sel
+                if attn.update or scores is None:                                     # attention.py:25-28
+                    ops.score_select(ws["qkv"].view(B, N, 3 * C), H, keep,
+                                     keep_idx=keep_idx, next_scores=next_scores, row_map=row_map)
+                else:
+                    ops.select(scores, keep, keep_idx=keep_idx, next_scores=next_scores, row_map=row_map)
+                ops.attention(ws["qkv"], row_map, B, N, Np, C, H, float(attn.scale), out=ws["att"])
+                # proj + gathered residual: x_new[b,j] = x[b, keep_idx[b,j]] + proj(att)   model.py:55-58
+                ops.gemm(ws["att"], pw, pb, B * Np, C, C, residual=cur, ldres=C, res_row_map=row_map, out=nxt, ldd=C)
+                cur, nxt = nxt, cur
+                scores = next_scores                                                  # attention.py:58
+                keep_log.append(keep_idx)
+                N = Np
+                M = B * N
+            else:
+                ops.attention(ws["qkv"], None, B, N, N, C, H, float(blk.attn.scale), out=ws["att"])
+                ops.gemm(ws["att"], pw, pb, M, C, C, residual=cur, ldres=C, out=cur, ldd=C)   # in place
+                scores = None                                                         # model.py:63
+                keep_log.append(None)
+            ops.layernorm(cur, g2, b2, e2, M, C, out=ws["xn"])                        # model.py:59
+            ops.gemm(ws["xn"], f1w, f1b, M, hidden, C, gelu=True, out=ws["hid"], ldd=hidden)
+            ops.gemm(ws["hid"], f2w, f2b, M, C, hidden, residual=cur, ldres=C, out=cur, ldd=C)
+
+        # ---- final norm on the CLS rows only (LayerNorm is row-wise) + head   model.py:65-66
+        gn, bn, en = pk.norm(m.norm)
+        hw, hb = pk.linear(m.head)
+        ops.layernorm(cur, gn, bn, en, B, C, in_row_stride=N * C, out=ws["cls"])
+        logits = ops.gemm(ws["cls"], hw, hb, B, hw.shape[0], C, out_f32=True)
+
+        self._last_stats = {"token_counts": token_counts}                            # model.py:68
+        self._last_keep_idx = keep_log
+        return logits if out_dtype == torch.float32 else logits.to(out_dtype)
