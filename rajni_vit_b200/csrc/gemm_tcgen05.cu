@@ -14,6 +14,7 @@
 //   warps 4-11: epilogue; warp w reads TMEM lanes 32*(w%4).. and column half (w-4)/4
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue).
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -25,12 +26,17 @@ constexpr int kGemmThreads = 384;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiStageBytes = 32 * 128;   // per-warp staging: 32 rows x 32 fp32
 
-template <int BN> struct GemmCfg {
-    static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+// CG = CTAs per MMA (tcgen05 cta_group): 1, or 2 = a CTA pair computing a 256 x BN tile together.
+// In pair mode each CTA stages its own 128 A rows and BN/2 of the B rows, so a CTA pulls
+// (128 + BN/2) x 64 bf16 from L2 per k-block instead of (128 + BN) x 64: the 1-CTA 128x256 tile is
+// L2-bandwidth bound on B200 (measured 11.7 TB/s of operand traffic at ~1000 TFLOP/s).
+template <int BN, int CG> struct GemmCfg {
+    static constexpr int kBRows = BN / CG;                  // B rows staged by each CTA
     static constexpr int kABytes = BM * BK * 2;
-    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kBBytes = kBRows * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kTmemCols = 2 * BN;               // double-buffered accumulator
+    static constexpr int kStages = (192 * 1024) / kStageBytes;
+    static constexpr int kTmemCols = 2 * BN;                // double-buffered accumulator
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 256 /*barriers*/ + 1024 /*align*/;
 };
 
@@ -65,68 +71,82 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return x >= 0.f ? x - s : s;
 }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_a = smem;                                        // [stages][128][64] bf16, SW128
-    uint8_t* s_b = smem + Cfg::kStages * Cfg::kABytes;          // [stages][BN][64] bf16, SW128
+    uint8_t* s_b = smem + Cfg::kStages * Cfg::kABytes;          // [stages][BN/CG][64] bf16, SW128
     uint8_t* s_epi = smem + Cfg::kStages * Cfg::kStageBytes;    // [8 warps][32][32] fp32
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + kEpiWarps * kEpiStageBytes);
-    uint64_t* full_bar = bars;                                  // [stages]
+    uint64_t* full_bar = bars;                                  // [stages]  (pair mode: the leader's is used)
     uint64_t* empty_bar = bars + Cfg::kStages;                  // [stages]
     uint64_t* tmem_full = bars + 2 * Cfg::kStages;              // [2]
-    uint64_t* tmem_empty = tmem_full + 2;                       // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                       // [2]       (pair mode: the leader's is used)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = p.tiles_m * p.tiles_n;
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int first_tile = blockIdx.x / CG, tile_stride = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps); }
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], CG); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps * CG); }
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    if (warp == 2) {
+        if (CG == 2) tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols);
+        else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer (one lane per CTA) =================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
                 const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+                const int row_a = m_blk * (BM * CG) + (int)cta_rank * BM;
+                const int row_b = n_blk * BN + (int)cta_rank * Cfg::kBRows;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                    tma_load_2d(s_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
-                    tma_load_2d(s_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (CG == 2) {
+                        const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        mbar_expect_tx_cluster(lead_bar, Cfg::kStageBytes);
+                        tma_load_2d_cg2(s_a + stage * Cfg::kABytes, &tmap_a, lead_bar, kb * BK, row_a);
+                        tma_load_2d_cg2(s_b + stage * Cfg::kBBytes, &tmap_b, lead_bar, kb * BK, row_b);
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                        tma_load_2d(s_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BK, row_a);
+                        tma_load_2d(s_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BK, row_b);
+                    }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+        // ================= MMA issuer (one lane of the leader CTA) =================
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+            for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++local) {
                 const int acc = local & 1;
                 const uint32_t acc_phase = (local >> 1) & 1;
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);          // epilogues have drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -139,12 +159,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         // advancing 16 bf16 along K = +32 bytes inside the 128-byte swizzle row
                         const uint64_t a_desc = umma_desc_sw128(a_addr + k * 32, 16, 1024);
                         const uint64_t b_desc = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-                        umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+                        if (CG == 2) umma_bf16_cg2(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+                        else umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty_bar[stage]);                  // frees the smem slot when these MMAs finish
+                    // frees the smem slot (in both CTAs of a pair) when these MMAs finish
+                    if (CG == 2) umma_commit_cg2(&empty_bar[stage], 0x3); else umma_commit(&empty_bar[stage]);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);                        // accumulator ready for the epilogue
+                // accumulator ready for the epilogue warps (of both CTAs)
+                if (CG == 2) umma_commit_cg2(&tmem_full[acc], 0x3); else umma_commit(&tmem_full[acc]);
             }
         }
     } else if (warp >= 4) {
@@ -160,14 +183,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int r_in = lane >> 3;                 // row within a group of 4 (phase 2)
         const int c4 = lane & 7;                    // 4-column group within the 32-column chunk
         int local = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++local) {
             const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
-            const int row0 = m_blk * BM + sub * 32;
-            // rows this lane stores in phase 2: row0 + it*4 + r_in
+            const int row0 = m_blk * (BM * CG) + (int)cta_rank * BM + sub * 32;
+            const int ncol0 = n_blk * BN + half * (BN / 2);
+            // rows this lane handles in phase 2: row0 + it*4 + r_in
             long long orow[8], rrow[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
@@ -180,9 +202,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     rrow[it] = 0;
                 }
             }
+            // pull this warp's residual slab towards L2 while the MMAs of this tile are still running
+            if (has_res) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int n = ncol0 + c4 * (BN / 16);
+                    if (orow[it] >= 0 && n < p.N) prefetch_l2(p.residual + rrow[it] * p.ldres + n);
+                }
+            }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
 #pragma unroll 1
             for (int ch = 0; ch < BN / 64; ++ch) {
                 const int col_in_tile = half * (BN / 2) + ch * 32;
+                const int n = n_blk * BN + col_in_tile + c4 * 4;
+                const bool full4 = (n + 4 <= p.N);
+                // residual loads first: their latency overlaps the TMEM read and the smem transpose
+                uint2 rres[8];
+                if (has_res && full4) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it)
+                        rres[it] = (orow[it] >= 0) ? __ldg(reinterpret_cast<const uint2*>(p.residual + rrow[it] * p.ldres + n))
+                                                   : make_uint2(0u, 0u);
+                }
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN + col_in_tile), v);
                 tmem_ld_wait();
@@ -195,10 +237,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 __syncwarp();
                 // phase 2: 8 lanes per row, 4 rows per instruction -> coalesced global traffic
-                const int n = n_blk * BN + col_in_tile + c4 * 4;
                 float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (has_bias && n < p.N) {
-                    if (n + 4 <= p.N) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                    if (full4) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
                     else {
                         bv.x = __ldg(p.bias + n);
                         if (n + 1 < p.N) bv.y = __ldg(p.bias + n + 1);
@@ -212,14 +253,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (orow[it] < 0 || n >= p.N) continue;
                     a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
                     if (do_gelu) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
-                    const bool full4 = (n + 4 <= p.N);
                     if (has_res) {
-                        const __nv_bfloat16* rp = p.residual + rrow[it] * p.ldres + n;
                         if (full4) {
-                            const uint2 rr = __ldg(reinterpret_cast<const uint2*>(rp));
-                            const float2 r0 = bf16x2_to_float2(rr.x), r1 = bf16x2_to_float2(rr.y);
+                            const float2 r0 = bf16x2_to_float2(rres[it].x), r1 = bf16x2_to_float2(rres[it].y);
                             a.x += r0.x; a.y += r0.y; a.z += r1.x; a.w += r1.y;
                         } else {
+                            const __nv_bfloat16* rp = p.residual + rrow[it] * p.ldres + n;
                             a.x += __bfloat162float(rp[0]);
                             if (n + 1 < p.N) a.y += __bfloat162float(rp[1]);
                             if (n + 2 < p.N) a.z += __bfloat162float(rp[2]);
@@ -247,15 +286,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+                else mbar_arrive(&tmem_empty[acc]);
+            }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
+        else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
@@ -303,25 +346,39 @@ static int num_sms() {
     return n;
 }
 
-template <int BN>
+template <int BN, int CG>
 static int launch_gemm(const void* A, const void* W, GemmParams& p, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CG>;
     CUtensorMap ta, tb;
     if (int rc = make_tmap_bf16_2d(&ta, A, p.M, p.K, p.K, BM)) return rc;
-    if (int rc = make_tmap_bf16_2d(&tb, W, p.N, p.K, p.K, BN)) return rc;
-    p.tiles_m = (p.M + BM - 1) / BM;
+    if (int rc = make_tmap_bf16_2d(&tb, W, p.N, p.K, p.K, Cfg::kBRows)) return rc;
+    p.tiles_m = (p.M + BM * CG - 1) / (BM * CG);
     p.tiles_n = (p.N + BN - 1) / BN;
     p.k_blocks = (p.K + BK - 1) / BK;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "gemm: smem attribute (%d B): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
         attr_done = true;
     }
-    int grid = p.tiles_m * p.tiles_n;
-    if (grid > num_sms()) grid = num_sms();
-    gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+    int grid = p.tiles_m * p.tiles_n * CG;
+    const int max_grid = (num_sms() / CG) * CG;
+    if (grid > max_grid) grid = max_grid;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG>, ta, tb, p);
     count_launch();
+    RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "gemm_bf16: launch failed: %s", cudaGetErrorString(e));
     return check_launch("gemm_bf16");
 }
 
@@ -351,9 +408,11 @@ extern "C" int rajni_gemm_bf16(const void* A, const void* W, const float* bias, 
     if (cost(128) < cost(bn)) bn = 128;
     if (cost(64) < cost(bn)) bn = 64;
     auto s = static_cast<cudaStream_t>(stream);
+    // wide problems run as CTA pairs (256 x 256 tiles); narrow ones keep single-CTA tiles
+    static const bool force_cg1 = getenv("RAJNI_GEMM_CG1") != nullptr;     // debugging aid
     switch (bn) {
-        case 256: return launch_gemm<256>(A, W, p, s);
-        case 128: return launch_gemm<128>(A, W, p, s);
-        default: return launch_gemm<64>(A, W, p, s);
+        case 256: return (M > BM && !force_cg1) ? launch_gemm<256, 2>(A, W, p, s) : launch_gemm<256, 1>(A, W, p, s);
+        case 128: return launch_gemm<128, 1>(A, W, p, s);
+        default: return launch_gemm<64, 1>(A, W, p, s);
     }
 }

@@ -42,7 +42,7 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
 
 // order-preserving float -> uint key (larger float => larger key; +NaN sorts largest like topk)
 __device__ __forceinline__ uint32_t float_key(float f) {
-    uint32_t u = __float_as_uint(f);
+    uint32_t u = __float_as_uint(f + 0.0f);        // -0.0 -> +0.0: they compare equal in the reference
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 

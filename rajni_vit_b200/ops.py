@@ -11,6 +11,43 @@ from . import _lib
 from ._lib import EPI_BIAS, EPI_GELU, EPI_OUT_F32, EPI_RESIDUAL  # noqa: F401  (re-exported)
 
 _checked_devices = set()
+_prof = None        # list of (name, work, start_event, end_event) while profile_steps() runs
+
+
+def _call(name: str, work: float, fn, *args) -> None:
+    """Launch one C-ABI kernel; under profile_steps() bracket it with CUDA events on the launch stream."""
+    if _prof is None:
+        _lib.check(fn(*args))
+        return
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    _lib.check(fn(*args))
+    end.record()
+    _prof.append((name, work, start, end))
+
+
+def profile_steps(step_fn, steps: int = 3):
+    """Run ``step_fn`` ``steps`` times with every kernel launch timed by its own CUDA-event pair.
+    Returns {kernel class: {"ms": per-step ms, "work": per-step flops or bytes, "launches": per step}}."""
+    global _prof
+    step_fn()
+    torch.cuda.synchronize()
+    _prof = []
+    try:
+        for _ in range(steps):
+            step_fn()
+        torch.cuda.synchronize()
+        out = {}
+        for name, work, s, e in _prof:
+            d = out.setdefault(name, {"ms": 0.0, "work": 0.0, "launches": 0})
+            d["ms"] += s.elapsed_time(e) / steps
+            d["work"] += work / steps
+            d["launches"] += 1
+        for d in out.values():
+            d["launches"] //= steps
+        return out
+    finally:
+        _prof = None
 
 
 def _stream(t: torch.Tensor) -> int:
@@ -39,8 +76,8 @@ def importance(qkv: torch.Tensor, num_heads: int, eps: float = 1e-6) -> torch.Te
     _bf16c(qkv)
     B, N, C3 = qkv.shape
     scores = torch.empty((B, N), device=qkv.device, dtype=torch.float32)
-    _lib.check(_lib.load().rajni_importance(qkv.data_ptr(), B, N, C3 // 3, num_heads, eps,
-                                            scores.data_ptr(), _stream(qkv)))
+    _call("score_select", B * (2 * N * (C3 // 3) * 2 + (C3 // 3) * 2 + 4 * N), _lib.load().rajni_importance,
+          qkv.data_ptr(), B, N, C3 // 3, num_heads, eps, scores.data_ptr(), _stream(qkv))
     return scores
 
 
@@ -54,8 +91,8 @@ def select(scores: torch.Tensor, keep: int, keep_idx=None, next_scores=None, row
     keep_idx = torch.empty((B, keep + 1), device=dev, dtype=torch.int32) if keep_idx is None else keep_idx
     next_scores = torch.empty((B, keep + 1), device=dev, dtype=torch.float32) if next_scores is None else next_scores
     row_map = torch.empty((B * (keep + 1),), device=dev, dtype=torch.int32) if row_map is None else row_map
-    _lib.check(_lib.load().rajni_select(scores.data_ptr(), B, N, keep, keep_idx.data_ptr(),
-                                        next_scores.data_ptr(), row_map.data_ptr(), _stream(scores)))
+    _call("select", B * (4 * N + 12 * (keep + 1)), _lib.load().rajni_select, scores.data_ptr(), B, N, keep,
+          keep_idx.data_ptr(), next_scores.data_ptr(), row_map.data_ptr(), _stream(scores))
     return keep_idx, next_scores, row_map
 
 
@@ -71,9 +108,11 @@ def score_select(qkv: torch.Tensor, num_heads: int, keep: int, eps: float = 1e-6
     keep_idx = torch.empty((B, keep + 1), device=dev, dtype=torch.int32) if keep_idx is None else keep_idx
     next_scores = torch.empty((B, keep + 1), device=dev, dtype=torch.float32) if next_scores is None else next_scores
     row_map = torch.empty((B * (keep + 1),), device=dev, dtype=torch.int32) if row_map is None else row_map
-    _lib.check(_lib.load().rajni_score_select(qkv.data_ptr(), B, N, C3 // 3, num_heads, keep, eps, _ptr(scores),
-                                              keep_idx.data_ptr(), next_scores.data_ptr(), row_map.data_ptr(),
-                                              _stream(qkv)))
+    C = C3 // 3
+    # algorithmic bytes: K and V planes + CLS query in, index + carried score out
+    _call("score_select", B * (2 * N * C * 2 + C * 2 + 8 * (keep + 1)), _lib.load().rajni_score_select,
+          qkv.data_ptr(), B, N, C, num_heads, keep, eps, _ptr(scores),
+          keep_idx.data_ptr(), next_scores.data_ptr(), row_map.data_ptr(), _stream(qkv))
     return scores, keep_idx, next_scores, row_map
 
 
@@ -82,8 +121,8 @@ def gather_rows(src: torch.Tensor, row_map: torch.Tensor, out: Optional[torch.Te
     _bf16c(src)
     rows_out, E = row_map.numel(), src.shape[-1]
     out = torch.empty((rows_out, E), device=src.device, dtype=torch.bfloat16) if out is None else out
-    _lib.check(_lib.load().rajni_gather_rows(src.data_ptr(), row_map.data_ptr(), out.data_ptr(), rows_out, E,
-                                             _stream(src)))
+    _call("gather_rows", rows_out * (4 * E + 4), _lib.load().rajni_gather_rows,
+          src.data_ptr(), row_map.data_ptr(), out.data_ptr(), rows_out, E, _stream(src))
     return out
 
 
@@ -91,8 +130,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
               in_row_stride: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Row LayerNorm, bf16 -> bf16; row r read at x.data_ptr + r*in_row_stride elements."""
     out = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16) if out is None else out
-    _lib.check(_lib.load().rajni_layernorm(x.data_ptr(), C if in_row_stride is None else in_row_stride,
-                                           gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(), rows, C, _stream(x)))
+    _call("layernorm", rows * C * 4, _lib.load().rajni_layernorm, x.data_ptr(),
+          C if in_row_stride is None else in_row_stride, gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(),
+          rows, C, _stream(x))
     return out
 
 
@@ -106,10 +146,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], M: int,
             (EPI_RESIDUAL if residual is not None else 0) | (EPI_OUT_F32 if out_f32 else 0)
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
-    _lib.check(_lib.load().rajni_gemm_bf16(
-        a.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, flags,
-        _ptr(residual), (N if ldres is None else ldres), _ptr(res_row_map),
-        (N if ldd is None else ldd), _ptr(out_row_map), _stream(a)))
+    _call("gemm", 2.0 * M * N * K, _lib.load().rajni_gemm_bf16,
+          a.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, flags,
+          _ptr(residual), (N if ldres is None else ldres), _ptr(res_row_map),
+          (N if ldd is None else ldd), _ptr(out_row_map), _stream(a))
     return out
 
 
@@ -117,8 +157,8 @@ def attention(qkv: torch.Tensor, row_map: Optional[torch.Tensor], B: int, N_src:
               num_heads: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Attention over the Np kept tokens of each image, gather fused.  -> [B*Np, C] bf16"""
     out = torch.empty((B * Np, C), device=qkv.device, dtype=torch.bfloat16) if out is None else out
-    _lib.check(_lib.load().rajni_attention_fwd(qkv.data_ptr(), _ptr(row_map), out.data_ptr(), B, N_src, Np, C,
-                                               num_heads, scale, _stream(qkv)))
+    _call("attention", 4.0 * B * Np * Np * C, _lib.load().rajni_attention_fwd,
+          qkv.data_ptr(), _ptr(row_map), out.data_ptr(), B, N_src, Np, C, num_heads, scale, _stream(qkv))
     return out
 
 
@@ -130,5 +170,6 @@ def patch_im2col(images: torch.Tensor, patch: int, cols: torch.Tensor, cls_pos0:
     B, ch, S, S2 = images.shape
     if ch != 3 or S != S2:
         raise ValueError(f"images must be [B,3,S,S], got {tuple(images.shape)}")
-    _lib.check(_lib.load().rajni_patch_im2col(images.data_ptr(), int(images.dtype == torch.float32), B, S, patch,
-                                              cols.data_ptr(), cls_pos0.data_ptr(), x.data_ptr(), C, _stream(images)))
+    _call("patch_im2col", images.numel() * images.element_size() + images.numel() * 2 + B * C * 2,
+          _lib.load().rajni_patch_im2col, images.data_ptr(), int(images.dtype == torch.float32), B, S, patch,
+          cols.data_ptr(), cls_pos0.data_ptr(), x.data_ptr(), C, _stream(images))

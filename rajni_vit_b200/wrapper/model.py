@@ -202,7 +202,7 @@ class RAJNIViTWrapper(nn.Module):
                     ws["sel"][i] = sel
                 keep_idx, next_scores, row_map = sel
                 if attn.update or scores is None:                                     # attention.py:25-28
-                    ops.score_select(ws["qkv"].view(B, N, 3 * C), H, keep,
+                    ops.score_select(ws["qkv"][: B * N].view(B, N, 3 * C), H, keep,
                                      keep_idx=keep_idx, next_scores=next_scores, row_map=row_map)
                 else:
                     ops.select(scores, keep, keep_idx=keep_idx, next_scores=next_scores, row_map=row_map)

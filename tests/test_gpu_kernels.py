@@ -215,20 +215,21 @@ def test_gemm(ops, M, N, K, gelu, res, maps, f32):
 
 
 def test_gelu_matches_erf(ops):
-    """The epilogue's GELU is a polynomial form of x*Phi(x); check it against erf over the whole useful range."""
+    """The epilogue's GELU is a polynomial form of x*Phi(x); check it against erf over the whole useful range.
+    acc = 0 (zero weights), so out[m, n] = gelu(bias[n]) exactly as the epilogue sees fp32 inputs."""
     K = 64
-    x = torch.linspace(-9, 9, 128 * 256)
     a = torch.zeros(128, K)
-    a[:, 0] = 1.0
     w = torch.zeros(256, K)
-    # out[m, n] = bias-free a[m,0]*w[n,0]; put x through the bias instead for exact fp32 inputs
-    out = ops.gemm(dev(a, torch.bfloat16), dev(w, torch.bfloat16), dev(x[:256].contiguous()), 128, 256, K, gelu=True, out_f32=True)
-    ref = torch.nn.functional.gelu(x[:256].double()).float()
-    torch.testing.assert_close(out[0].cpu(), ref, rtol=1e-4, atol=2e-6)
-    for lo in range(0, 128 * 256, 256 * 16):
-        xb = x[lo::128][:256].contiguous()
+    x = torch.linspace(-9, 9, 256 * 64)
+    worst = 0.0
+    for i in range(64):
+        xb = x[i::64].contiguous()
         out = ops.gemm(dev(a, torch.bfloat16), dev(w, torch.bfloat16), dev(xb), 128, 256, K, gelu=True, out_f32=True)
-        torch.testing.assert_close(out[5].cpu(), torch.nn.functional.gelu(xb.double()).float(), rtol=1e-4, atol=2e-6)
+        ref = torch.nn.functional.gelu(xb.double())
+        got = out[i % 128].cpu().double()
+        worst = max(worst, ((got - ref).abs() / ref.abs().clamp_min(1e-3)).max().item())
+        torch.testing.assert_close(got, ref, rtol=1e-4, atol=2e-6)
+    print(f"gelu worst error relative to max(|ref|,1e-3): {worst:.2e}")
 
 
 # ------------------------------------------------------------------ attention
