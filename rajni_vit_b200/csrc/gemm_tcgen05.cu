@@ -71,7 +71,21 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return x >= 0.f ? x - s : s;
 }
 
-template <int BN, int CG>
+// explicit shared-state-space accesses (a generic pointer into dynamic smem compiles to LD.E/ST.E)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+// Epilogue modes: the three hot ones are compiled without any per-element flag or column-tail
+// logic (they require N % BN == 0); MODE_GENERIC reads the runtime flags and handles every edge.
+enum { MODE_GENERIC = 0, MODE_BIAS = 1, MODE_BIAS_GELU = 2, MODE_BIAS_RES = 3 };
+
+template <int BN, int CG, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
@@ -175,114 +189,145 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int ew = warp - 4;
         const int sub = warp & 3;                   // TMEM sub-partition = warp id % 4
         const int half = ew >> 2;                   // which half of the BN columns
-        float* stg = reinterpret_cast<float*>(s_epi + ew * kEpiStageBytes);
-        const bool has_bias = (p.flags & RAJNI_EPI_BIAS) != 0;
-        const bool do_gelu = (p.flags & RAJNI_EPI_GELU) != 0;
-        const bool has_res = (p.flags & RAJNI_EPI_RESIDUAL) != 0;
-        const bool out_f32 = (p.flags & RAJNI_EPI_OUT_F32) != 0;
+        const uint32_t stg = smem_u32(s_epi + ew * kEpiStageBytes);
+        const bool has_bias = MODE != MODE_GENERIC || (p.flags & RAJNI_EPI_BIAS) != 0;
+        const bool do_gelu = MODE == MODE_BIAS_GELU || (MODE == MODE_GENERIC && (p.flags & RAJNI_EPI_GELU) != 0);
+        const bool has_res = MODE == MODE_BIAS_RES || (MODE == MODE_GENERIC && (p.flags & RAJNI_EPI_RESIDUAL) != 0);
+        const bool out_f32 = MODE == MODE_GENERIC && (p.flags & RAJNI_EPI_OUT_F32) != 0;
         const int r_in = lane >> 3;                 // row within a group of 4 (phase 2)
         const int c4 = lane & 7;                    // 4-column group within the 32-column chunk
+        // phase-1 / phase-2 staging addresses (XOR swizzle on 16-byte slots; both conflict-free)
+        uint32_t st_addr[8], ld_addr[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) st_addr[c] = stg + lane * 128 + ((c ^ (lane & 7)) << 4);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + r_in;
+            ld_addr[it] = stg + r * 128 + ((c4 ^ (r & 7)) << 4);
+        }
         int local = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++local) {
             const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
             const int row0 = m_blk * (BM * CG) + (int)cta_rank * BM + sub * 32;
-            const int ncol0 = n_blk * BN + half * (BN / 2);
+            const int ncol0 = n_blk * BN + half * (BN / 2) + c4 * 4;     // this lane's first column
             // rows this lane handles in phase 2: row0 + it*4 + r_in
-            long long orow[8], rrow[8];
+            uint32_t valid = 0;
+            long long ooff[8], roff[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const int m = row0 + it * 4 + r_in;
+                ooff[it] = 0;
+                roff[it] = 0;
                 if (m < p.M) {
-                    orow[it] = p.out_row_map ? (long long)__ldg(p.out_row_map + m) : (long long)m;
-                    rrow[it] = has_res ? (p.res_row_map ? (long long)__ldg(p.res_row_map + m) : (long long)m) : 0;
-                } else {
-                    orow[it] = -1;
-                    rrow[it] = 0;
+                    valid |= 1u << it;
+                    ooff[it] = (p.out_row_map ? (long long)__ldg(p.out_row_map + m) : (long long)m) * p.ldd + ncol0;
+                    if (has_res)
+                        roff[it] = (p.res_row_map ? (long long)__ldg(p.res_row_map + m) : (long long)m) * p.ldres + ncol0;
                 }
             }
             // pull this warp's residual slab towards L2 while the MMAs of this tile are still running
             if (has_res) {
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int n = ncol0 + c4 * (BN / 16);
-                    if (orow[it] >= 0 && n < p.N) prefetch_l2(p.residual + rrow[it] * p.ldres + n);
-                }
+                for (int it = 0; it < 8; ++it)
+                    if ((valid >> it) & 1) prefetch_l2(p.residual + roff[it] - c4 * 4 + c4 * (BN / 16));
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
             for (int ch = 0; ch < BN / 64; ++ch) {
-                const int col_in_tile = half * (BN / 2) + ch * 32;
-                const int n = n_blk * BN + col_in_tile + c4 * 4;
-                const bool full4 = (n + 4 <= p.N);
-                // residual loads first: their latency overlaps the TMEM read and the smem transpose
-                uint2 rres[8];
-                if (has_res && full4) {
+                const int n = ncol0 + ch * 32;
+                const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2) + ch * 32);
+                if (MODE != MODE_GENERIC) {
+                    // ---------- hot path: no column tails, flags known at compile time ----------
+                    uint2 rres[8];
+                    if (MODE == MODE_BIAS_RES) {
 #pragma unroll
-                    for (int it = 0; it < 8; ++it)
-                        rres[it] = (orow[it] >= 0) ? __ldg(reinterpret_cast<const uint2*>(p.residual + rrow[it] * p.ldres + n))
-                                                   : make_uint2(0u, 0u);
-                }
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN + col_in_tile), v);
-                tmem_ld_wait();
-                // phase 1: thread = row; write 8 x 16 B with an XOR swizzle (conflict-free)
-                {
-                    uint4* rowp = reinterpret_cast<uint4*>(stg + lane * 32);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        rowp[c ^ (lane & 7)] = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                }
-                __syncwarp();
-                // phase 2: 8 lanes per row, 4 rows per instruction -> coalesced global traffic
-                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (has_bias && n < p.N) {
-                    if (full4) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                    else {
-                        bv.x = __ldg(p.bias + n);
-                        if (n + 1 < p.N) bv.y = __ldg(p.bias + n + 1);
-                        if (n + 2 < p.N) bv.z = __ldg(p.bias + n + 2);
+                        for (int it = 0; it < 8; ++it)
+                            rres[it] = ((valid >> it) & 1) ? __ldg(reinterpret_cast<const uint2*>(p.residual + roff[it] + ch * 32))
+                                                           : make_uint2(0u, 0u);
                     }
-                }
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                    uint32_t v[32];
+                    tmem_ld32(taddr, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int r = it * 4 + r_in;
-                    float4 a = *reinterpret_cast<const float4*>(stg + r * 32 + ((c4 ^ (r & 7)) << 2));
-                    if (orow[it] < 0 || n >= p.N) continue;
-                    a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
-                    if (do_gelu) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
-                    if (has_res) {
-                        if (full4) {
+                    for (int c = 0; c < 8; ++c) sts128(st_addr[c], v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    __syncwarp();
+                    float4 a[8];
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) a[it] = lds128(ld_addr[it]);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        float4 t = a[it];
+                        t.x += bv.x; t.y += bv.y; t.z += bv.z; t.w += bv.w;
+                        if (MODE == MODE_BIAS_GELU) { t.x = gelu_erf(t.x); t.y = gelu_erf(t.y); t.z = gelu_erf(t.z); t.w = gelu_erf(t.w); }
+                        if (MODE == MODE_BIAS_RES) {
                             const float2 r0 = bf16x2_to_float2(rres[it].x), r1 = bf16x2_to_float2(rres[it].y);
-                            a.x += r0.x; a.y += r0.y; a.z += r1.x; a.w += r1.y;
+                            t.x += r0.x; t.y += r0.y; t.z += r1.x; t.w += r1.y;
+                        }
+                        if ((valid >> it) & 1)
+                            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.D) + ooff[it] + ch * 32) =
+                                make_uint2(float2_to_bf16x2(t.x, t.y), float2_to_bf16x2(t.z, t.w));
+                    }
+                    __syncwarp();           // staging is overwritten by the next chunk
+                } else {
+                    // ---------- generic path: runtime flags, column tails, fp32 output ----------
+                    const bool full4 = (n + 4 <= p.N);
+                    uint32_t v[32];
+                    tmem_ld32(taddr, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) sts128(st_addr[c], v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    __syncwarp();
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_bias && n < p.N) {
+                        if (full4) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                        else {
+                            bv.x = __ldg(p.bias + n);
+                            if (n + 1 < p.N) bv.y = __ldg(p.bias + n + 1);
+                            if (n + 2 < p.N) bv.z = __ldg(p.bias + n + 2);
+                        }
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        float4 a = lds128(ld_addr[it]);
+                        if (!((valid >> it) & 1) || n >= p.N) continue;
+                        a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
+                        if (do_gelu) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+                        if (has_res) {
+                            const __nv_bfloat16* rp = p.residual + roff[it] + ch * 32;
+                            if (full4) {
+                                const uint2 rr = __ldg(reinterpret_cast<const uint2*>(rp));
+                                const float2 r0 = bf16x2_to_float2(rr.x), r1 = bf16x2_to_float2(rr.y);
+                                a.x += r0.x; a.y += r0.y; a.z += r1.x; a.w += r1.y;
+                            } else {
+                                a.x += __bfloat162float(rp[0]);
+                                if (n + 1 < p.N) a.y += __bfloat162float(rp[1]);
+                                if (n + 2 < p.N) a.z += __bfloat162float(rp[2]);
+                            }
+                        }
+                        if (out_f32) {
+                            float* dp = static_cast<float*>(p.D) + ooff[it] + ch * 32;
+                            if (full4) *reinterpret_cast<float4*>(dp) = a;
+                            else {
+                                dp[0] = a.x;
+                                if (n + 1 < p.N) dp[1] = a.y;
+                                if (n + 2 < p.N) dp[2] = a.z;
+                            }
                         } else {
-                            const __nv_bfloat16* rp = p.residual + rrow[it] * p.ldres + n;
-                            a.x += __bfloat162float(rp[0]);
-                            if (n + 1 < p.N) a.y += __bfloat162float(rp[1]);
-                            if (n + 2 < p.N) a.z += __bfloat162float(rp[2]);
+                            __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(p.D) + ooff[it] + ch * 32;
+                            if (full4) *reinterpret_cast<uint2*>(dp) = make_uint2(float2_to_bf16x2(a.x, a.y), float2_to_bf16x2(a.z, a.w));
+                            else {
+                                dp[0] = __float2bfloat16(a.x);
+                                if (n + 1 < p.N) dp[1] = __float2bfloat16(a.y);
+                                if (n + 2 < p.N) dp[2] = __float2bfloat16(a.z);
+                            }
                         }
                     }
-                    if (out_f32) {
-                        float* dp = static_cast<float*>(p.D) + orow[it] * p.ldd + n;
-                        if (full4) *reinterpret_cast<float4*>(dp) = a;
-                        else {
-                            dp[0] = a.x;
-                            if (n + 1 < p.N) dp[1] = a.y;
-                            if (n + 2 < p.N) dp[2] = a.z;
-                        }
-                    } else {
-                        __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(p.D) + orow[it] * p.ldd + n;
-                        if (full4) *reinterpret_cast<uint2*>(dp) = make_uint2(float2_to_bf16x2(a.x, a.y), float2_to_bf16x2(a.z, a.w));
-                        else {
-                            dp[0] = __float2bfloat16(a.x);
-                            if (n + 1 < p.N) dp[1] = __float2bfloat16(a.y);
-                            if (n + 2 < p.N) dp[2] = __float2bfloat16(a.z);
-                        }
-                    }
+                    __syncwarp();
                 }
-                __syncwarp();           // staging is overwritten by the next chunk
             }
             tc_fence_before();
             __syncwarp();
@@ -346,8 +391,8 @@ static int num_sms() {
     return n;
 }
 
-template <int BN, int CG>
-static int launch_gemm(const void* A, const void* W, GemmParams& p, cudaStream_t stream) {
+template <int BN, int CG, int MODE>
+static int launch_gemm_mode(const void* A, const void* W, GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, CG>;
     CUtensorMap ta, tb;
     if (int rc = make_tmap_bf16_2d(&ta, A, p.M, p.K, p.K, BM)) return rc;
@@ -357,7 +402,7 @@ static int launch_gemm(const void* A, const void* W, GemmParams& p, cudaStream_t
     p.k_blocks = (p.K + BK - 1) / BK;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "gemm: smem attribute (%d B): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
         attr_done = true;
     }
@@ -376,10 +421,24 @@ static int launch_gemm(const void* A, const void* W, GemmParams& p, cudaStream_t
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG>, ta, tb, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG, MODE>, ta, tb, p);
     count_launch();
     RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "gemm_bf16: launch failed: %s", cudaGetErrorString(e));
     return check_launch("gemm_bf16");
+}
+
+// pick the compile-time epilogue when the problem has no column tail and a hot flag combination
+template <int BN, int CG>
+static int launch_gemm(const void* A, const void* W, GemmParams& p, cudaStream_t stream) {
+    if (p.N % BN == 0) {
+        switch (p.flags) {
+            case RAJNI_EPI_BIAS: return launch_gemm_mode<BN, CG, MODE_BIAS>(A, W, p, stream);
+            case RAJNI_EPI_BIAS | RAJNI_EPI_GELU: return launch_gemm_mode<BN, CG, MODE_BIAS_GELU>(A, W, p, stream);
+            case RAJNI_EPI_BIAS | RAJNI_EPI_RESIDUAL: return launch_gemm_mode<BN, CG, MODE_BIAS_RES>(A, W, p, stream);
+            default: break;
+        }
+    }
+    return launch_gemm_mode<BN, CG, MODE_GENERIC>(A, W, p, stream);
 }
 
 }  // namespace rajni
