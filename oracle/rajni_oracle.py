@@ -99,11 +99,15 @@ def mha(qkv: Tensor, num_heads: int, scale: float) -> Tensor:
 
 
 def pruned_attention(x_norm: Tensor, prev_scores: Optional[Tensor], blk: Dict[str, Tensor],
-                     num_heads: int, keep_ratio: float, update: bool
+                     num_heads: int, keep_ratio: float, update: bool,
+                     forced_idx: Optional[Tensor] = None
                      ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """RAJNIAttention.forward.   rajni/wrapper/attention.py:17-60
 
     Returns (out [B,Np,C], keep_idx [B,Np] int64, next_scores [B,Np], scores [B,N]).
+    ``forced_idx`` (tests only) replaces the selection with a given kept-token index so the
+    arithmetic downstream of the cut can be compared without selection noise; the oracle's own
+    scores are still computed and returned.
     """
     B, N, C = x_norm.shape
     qkv = F.linear(x_norm, blk["qkv_w"], blk["qkv_b"])                  # attention.py:22
@@ -112,7 +116,8 @@ def pruned_attention(x_norm: Tensor, prev_scores: Optional[Tensor], blk: Dict[st
     else:
         scores = prev_scores
     keep = keep_count(N, keep_ratio)
-    keep_idx = select(scores, keep)
+    keep_idx = select(scores, keep) if forced_idx is None else forced_idx.to(torch.long)
+    assert keep_idx.shape == (B, keep + 1)
     kept = torch.gather(qkv, 1, keep_idx[:, :, None].expand(-1, -1, 3 * C))   # attention.py:42-43
     scale = (C // num_heads) ** -0.5
     out = F.linear(mha(kept, num_heads, scale), blk["proj_w"], blk["proj_b"])   # attention.py:55
@@ -188,25 +193,27 @@ def mlp(x: Tensor, blk: Dict) -> Tensor:
     return F.linear(F.gelu(F.linear(h, blk["fc1_w"], blk["fc1_b"])), blk["fc2_w"], blk["fc2_b"])
 
 
-def pruned_block(x: Tensor, scores: Optional[Tensor], blk: Dict, keep_ratio: float, update: bool):
+def pruned_block(x: Tensor, scores: Optional[Tensor], blk: Dict, keep_ratio: float, update: bool,
+                 forced_idx: Optional[Tensor] = None):
     """Pruned block: LN1 -> pruned attention -> gather residual -> + -> MLP -> +.  model.py:50-59"""
     C = x.shape[-1]
     h = F.layer_norm(x, (C,), blk["n1_w"], blk["n1_b"], blk["n1_eps"])
     out, keep_idx, next_scores, full_scores = pruned_attention(
-        h, scores, blk, blk["num_heads"], keep_ratio, update)
+        h, scores, blk, blk["num_heads"], keep_ratio, update, forced_idx)
     x = torch.gather(x, 1, keep_idx[:, :, None].expand(-1, -1, C)) + out
     x = x + mlp(x, blk)
     return x, keep_idx, next_scores, full_scores
 
 
 @torch.no_grad()
-def forward(params: Dict, images: Tensor, schedule: Dict, trace: Optional[List] = None
-            ) -> Tuple[Tensor, Dict]:
+def forward(params: Dict, images: Tensor, schedule: Dict, trace: Optional[List] = None,
+            forced_keep: Optional[List[Optional[Tensor]]] = None) -> Tuple[Tensor, Dict]:
     """RAJNIViTWrapper.forward.   rajni/wrapper/model.py:30-69
 
     Returns (logits [B,classes], {"token_counts": [...]}); if ``trace`` is a list it
     receives one dict per block (block input, keep_idx, scores, output) for
-    teacher-forced comparisons.
+    teacher-forced comparisons.  ``forced_keep`` (one entry per block, None on un-pruned blocks)
+    teacher-forces the selection, see ``pruned_attention``.
     """
     sched = normalise_schedule(schedule)
     x = embed(params, images)
@@ -218,7 +225,8 @@ def forward(params: Dict, images: Tensor, schedule: Dict, trace: Optional[List] 
         if i in sched:
             ratio, update = sched[i]
             prev = scores
-            x, keep_idx, scores, full = pruned_block(x, scores, blk, ratio, update)
+            forced = forced_keep[i] if forced_keep is not None else None
+            x, keep_idx, scores, full = pruned_block(x, scores, blk, ratio, update, forced)
             if rec is not None:
                 rec.update(pruned=True, keep_idx=keep_idx, scores=full, prev_scores=prev,
                            next_scores=scores)

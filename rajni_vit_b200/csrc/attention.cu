@@ -9,6 +9,8 @@
 // (conflict-free ldmatrix).  The gather costs nothing extra: every 128-byte head slice of
 // a token row is fetched by its own row index.  (The tcgen05/TMEM version of this kernel is
 // the next step; attention is 3-9 % of the path's flops, the GEMMs went first.)
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rajni {
@@ -189,6 +191,9 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const AttnParams
     }
 }
 
+int launch_attention_tc(const void* qkv, const int32_t* row_map, void* out, int B, int N_src, int Np,
+                        int C, int H, float scale, cudaStream_t stream);   // attention_tc.cu
+
 }  // namespace rajni
 
 using namespace rajni;
@@ -200,6 +205,13 @@ extern "C" int rajni_attention_fwd(const void* qkv, const int32_t* row_map, void
                   "rajni_attention_fwd: B=%d N_src=%d Np=%d C=%d H=%d (head dim must be 64)", B, N_src, Np, C, H);
     RAJNI_REQUIRE(row_map || N_src == Np, RAJNI_EINVAL, "rajni_attention_fwd: N_src != Np needs a row_map");
     RAJNI_REQUIRE(B <= 65535 && H <= 65535, RAJNI_EINVAL, "rajni_attention_fwd: B or H exceeds grid limits");
+    // tcgen05 kernel for sequences that fit one TMEM score tile (every 224-px config); the mma.sync
+    // kernel below covers longer sequences (577-token config) until the multi-block version lands.
+    static const bool legacy = getenv("RAJNI_ATTN_LEGACY") != nullptr;
+    if (!legacy) {
+        int rc = launch_attention_tc(qkv, row_map, out, B, N_src, Np, C, H, scale, static_cast<cudaStream_t>(stream));
+        if (rc != 0) return rc < 0 ? rc : RAJNI_OK;
+    }
     AttnParams p{};
     p.qkv = static_cast<const __nv_bfloat16*>(qkv);
     p.row_map = row_map;

@@ -141,28 +141,65 @@ def test_errors(pkg):
         pkg.RAJNIViTWrapper(base, {})
 
 
+def near_tie_mismatch(ours: torch.Tensor, ref_scores: torch.Tensor, keep: int, rel_gap: float):
+    """Compare a kept-index set with the oracle's own scores on the same block input.
+
+    Returns (overlap fraction, worst relative distance to the cut of any token the two sides
+    disagree on).  A disagreement is legitimate only if the token sits within ``rel_gap`` of the
+    k-th score: bf16 activations perturb the scores by O(1e-2) relative, and random-init scores are
+    nearly flat, so tokens that close to the cut can swap."""
+    B = ours.shape[0]
+    worst, overlap = 0.0, 0.0
+    for b in range(B):
+        s = ref_scores[b, 1:].double()
+        cut = torch.sort(s, descending=True).values[keep - 1].item()
+        ref_set = set((torch.sort(s, descending=True, stable=True).indices[:keep] + 1).tolist())
+        our_set = set(ours[b, 1:].tolist())
+        overlap += len(ref_set & our_set) / keep
+        for t in ref_set ^ our_set:
+            worst = max(worst, abs(s[t - 1].item() - cut) / abs(cut))
+    return overlap / B, worst
+
+
 @pytest.mark.parametrize("name,sched,batch", [("vit_base_patch16_224", README_SCHEDULE, 16),
                                               ("vit_small_patch16_224", C3_SCHEDULE, 16)])
 def test_forward_vs_oracle_full_models(pkg, name, sched, batch):
-    """BASELINE configs 2 and 3 at a batch the CPU oracle finishes in seconds."""
+    """BASELINE configs 2 and 3 at a batch the CPU oracle finishes in seconds.
+
+    End-to-end drift on random-init weights is dominated by selection noise (the reference's own
+    fp32-vs-bf16 runs diverge the same way), so the comparison is teacher-forced:
+      1. arithmetic: the oracle is run with OUR kept indices forced at every pruned block; logits must
+         agree within bf16 tolerance (max |dlogit| < 0.08 at logit std ~0.57, top-1 agreement >= 0.9);
+      2. selection: at every pruned block the oracle's own fp32 scores on that same input must rank
+         our kept tokens identically except for tokens within 3 % of the cut score;
+      3. token_counts exact.  The free-running comparison is printed for the record."""
     from rajni_vit_b200.vit import create_model
     base = create_model(name, seed=0)
     params = orc.extract_params(copy.deepcopy(base))
     model = pkg.RAJNIViTWrapper(base, sched).cuda().eval()
     images = make_images(batch, 224, 1234)
     logits = model(images.cuda()).cpu()
+    ours = [None if k is None else k.cpu().long() for k in model._last_keep_idx]
+    for k in ours:
+        if k is not None:
+            assert (k[:, 0] == 0).all() and (k[:, 1:] > k[:, :-1]).all()
     trace = []
-    ref, stats = orc.forward(params, images, sched, trace=trace)
+    ref, stats = orc.forward(params, images, sched, trace=trace, forced_keep=ours)
     assert model.get_last_stats() == stats
     err = (logits - ref).abs().max().item()
     agree = (logits.argmax(1) == ref.argmax(1)).float().mean().item()
-    print(f"{name}: max |dlogit| {err:.4f}, top-1 agreement {agree:.3f}, logit std {ref.std():.3f}")
-    for rec, kidx in zip(trace, model._last_keep_idx):
-        if kidx is not None:
-            ov = np.mean([len(set(a.tolist()) & set(b.tolist())) / len(b)
-                          for a, b in zip(kidx.cpu().numpy(), rec["keep_idx"].numpy())])
-            print(f"  block {rec['block']}: kept-set overlap {ov:.4f}")
-    assert err < 0.12 and agree >= 0.8
+    print(f"{name} (selection teacher-forced): max |dlogit| {err:.4f}, top-1 agreement {agree:.3f}, logit std {ref.std():.3f}")
+    assert err < 0.08 and agree >= 0.9
+    for rec, kidx in zip(trace, ours):
+        if kidx is None:
+            continue
+        keep = kidx.shape[1] - 1
+        ov, worst = near_tie_mismatch(kidx, rec["scores"], keep, 0.03)
+        print(f"  block {rec['block']}: kept-set overlap {ov:.4f}, worst disagreeing token is {worst:.2e} (relative) from the cut")
+        assert worst < 0.03
+    free, _ = orc.forward(params, images, sched)
+    print(f"{name} (free-running): max |dlogit| {(logits - free).abs().max().item():.4f}, "
+          f"top-1 agreement {(logits.argmax(1) == free.argmax(1)).float().mean().item():.3f}")
 
 
 def test_full_batch_properties(pkg):
