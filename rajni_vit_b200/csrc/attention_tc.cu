@@ -1,178 +1,455 @@
-// tcgen05 attention over kept tokens, one CTA per (image, head), Np <= 256 keys.
+// Persistent, warp-specialised tcgen05 attention over kept tokens (Np <= 256 keys, head dim 64).
 //
 //   out[b, i, h*64:(h+1)*64] = softmax_j( q_i . k_j * scale ) v_j        attention.py:45-54
 //   token j of image b is read from global qkv row row_map[b*Np + j]     attention.py:42-43 (gather fused)
 //
-// Per CTA: the head's Q (up to 2 tiles of 128 rows), K and V slices are gathered row by row into
-// 128-byte-swizzled shared memory with cp.async (every row is one 128 B head slice; rows past Np are
-// zero-filled).  Then for each 128-query tile
-//   S = Q K^T       : tcgen05.mma, A = Q (K-major), B = K (K-major), N = Np rounded to 16, fp32 in TMEM
-//   P = softmax(S)  : 128 threads, one row each, two passes over the TMEM row; P is written back to
-//                     TMEM as packed bf16 (aliasing the S columns already consumed)
-//   O = P V         : tcgen05.mma with A = P from TMEM and B = V from smem (MN-major), N = 64
-//   epilogue        : O * (1/rowsum) -> bf16 -> global
-// TMEM: 256 columns per CTA (S at [0,256), P at [0,128), O at [128,192)); ~85 KB smem => 2 CTAs per SM,
-// which is what overlaps one CTA's gather/softmax with the other's MMAs.
+// One CTA per SM loops over work units.  A unit fills the two 128-row score tiles of the SM:
+//   Np > 128 : one (image, head); tile 0 = queries 0..127, tile 1 = queries 128..Np-1, shared K/V
+//   Np <= 128: two (image, head) pairs, one per tile, each with its own K/V
+// Roles (416 threads):
+//   warps 0-3 / 4-7 : softmax + epilogue of tile 0 / tile 1 (thread = query row = TMEM lane)
+//   warp 8          : tcgen05.mma issuer (one lane), an event loop over the two tiles
+//   warps 9-12      : loaders into 128-byte-swizzled shared memory, 2-4 stages deep, Q/K and V on separate
+//                     barriers.  Dense call (no row map): one TMA box per plane.  Gathered call: cp.async row
+//                     gather of the head's Q/K/V slices (128 B per token from arbitrary global rows), so the
+//                     kept-token gather needs no separate pass over HBM
+// Per tile:  S = Q K^T (SS MMA, fp32 in TMEM) -> two passes over the TMEM row (max; exp2/sum) ->
+//            P written back over S as packed bf16 -> O = P V (TS MMA: A from TMEM, V MN-major from smem)
+//            -> O/rowsum -> bf16 -> 32-byte global stores.
+// TMEM: 512 columns = 2 tiles x 256: S at [0,Np_pad), P at [0,Np_pad/2), O at [192,256) when Np_pad <= 192
+// (then S of the next unit never waits for the O read-out), else at [128,192).
+// Measured on B200 (tools/probes/mma_probe.cu): a tcgen05.mma with M=128 costs >= 94 cycles whatever N is,
+// so the N=64 PV products run at a third of the tensor peak; with MUFU.EX2 at 16/clk/SM the softmax costs
+// about as much.  The kernel is built to overlap the two, not to reach the GEMM roofline.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace rajni {
 
-constexpr int kTcThreads = 160;          // warps 0-3: loads + softmax (one TMEM sub-partition each); warp 4: MMA issuer
-constexpr int kTcTmemCols = 256;
-constexpr int kTcOCol = 128;
+constexpr int kAtSoftmaxWarps = 8;
+constexpr int kAtMmaWarp = 8;
+constexpr int kAtLoaderWarp0 = 9;
+constexpr int kAtLoaderThreads = 128;
+constexpr int kAtThreads = (kAtSoftmaxWarps + 1) * 32 + kAtLoaderThreads;     // 416
+constexpr int kAtMaxStages = 4;
+constexpr int kAtTileCols = 256;
+constexpr int kAtSmemBudget = 224 * 1024;                                     // stages; barriers and alignment on top
+
+// Optional event trace (tools/probes/attn_trace.cu builds this file with -DRAJNI_ATTN_TRACE): clock64 stamps of
+// CTA 0's pipeline events, one row of 32 slots per unit.  Compiles to nothing in the library.
+#ifdef RAJNI_ATTN_TRACE
+__device__ long long g_attn_trace[64 * 32];
+#define AT_TRACE(n, slot) do { if (blockIdx.x == 0 && (n) < 64) g_attn_trace[(n) * 32 + (slot)] = clock64(); } while (0)
+#else
+#define AT_TRACE(n, slot) do { } while (0)
+#endif
 
 struct AttnTcParams {
     const __nv_bfloat16* qkv;
     const int32_t* row_map;
     __nv_bfloat16* out;
-    int N_src, Np, Np_pad, C, H, nqt;
+    int N_src, Np, Np_pad, C, H, BH, two_tiles, n_units;
+    int o_col, o_outside;       // TMEM column of O inside a tile; o_outside = O does not overlap S's columns
+    int plane_bytes, stages;    // bytes of one Q/K/V plane of a stage (1024-aligned); pipeline depth
     float scale_log2;
 };
 
-__device__ __forceinline__ void cp_async16_zfill(uint32_t smem_dst, const void* gsrc, bool valid) {
-    const int bytes = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_dst), "l"(gsrc), "r"(bytes) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+// arrive on `bar` once every cp.async issued so far by this thread has landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
-__global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnTcParams p) {
+// (image*H + head) handled by tile `t` of unit `u`, or -1
+__device__ __forceinline__ int unit_item(const AttnTcParams& p, int u, int t) {
+    if (p.two_tiles) return u;
+    const int item = 2 * u + t;
+    return item < p.BH ? item : -1;
+}
+
+__global__ void __launch_bounds__(kAtThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int q_rows = p.nqt * 128;
-    const uint32_t s_q = smem_base;                                 // [q_rows][128 B]
-    const uint32_t s_k = s_q + q_rows * 128;                        // [Np_pad][128 B]
-    const uint32_t s_v = s_k + ((p.Np_pad * 128 + 1023) & ~1023);   // [Np_pad][128 B]
-    __shared__ __align__(8) uint64_t bar_s, bar_o, bar_p, bar_done;
-    __shared__ uint32_t tmem_slot;
-    __shared__ int s_rows[256];             // global qkv row of every kept token of this image
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int stage_bytes = 3 * p.plane_bytes;
+    // (tile 1's Q operand is read as 128 rows from row 128 of its plane: the over-read lands in the stage's K plane)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + p.stages * stage_bytes);
+    uint64_t* qk_full = bars;                      // [4] loader -> MMA   (TMA transaction bytes of Q and K)
+    uint64_t* v_full = bars + kAtMaxStages;        // [4] loader -> MMA   (V)
+    uint64_t* empty_bar = bars + 2 * kAtMaxStages; // [4] MMA -> loader   (tcgen05.commit)
+    uint64_t* s_full = bars + 3 * kAtMaxStages;    // [2 tiles] MMA -> softmax (S ready)
+    uint64_t* p_full = s_full + 2;                 // [2 tiles] softmax -> MMA (P in TMEM, 128 arrivals)
+    uint64_t* o_full = s_full + 4;                 // [2 tiles] MMA -> softmax (O ready)
+    uint64_t* o_empty = s_full + 6;                // [2 tiles] softmax -> MMA (O read out)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
 
-    const int h = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    if (warp == 4) {
-        tmem_alloc(&tmem_slot, kTcTmemCols);
+    if (warp == kAtMmaWarp) {
+        tmem_alloc(tmem_slot, 512);
         if (lane == 0) {
-            mbar_init(&bar_s, 1);
-            mbar_init(&bar_o, 1);
-            mbar_init(&bar_p, 128);
-            mbar_init(&bar_done, 128);
+            for (int i = 0; i < kAtMaxStages; ++i) {
+                // gathered: one cp.async-completion arrival per loader thread; dense: one arrival + TMA transaction bytes
+                mbar_init(&qk_full[i], p.row_map ? kAtLoaderThreads : 1);
+                mbar_init(&v_full[i], p.row_map ? kAtLoaderThreads : 1);
+                mbar_init(&empty_bar[i], 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&s_full[i], 1);
+                mbar_init(&p_full[i], 128);
+                mbar_init(&o_full[i], 1);
+                mbar_init(&o_empty[i], 128);
+            }
             mbar_fence_init();
         }
-    }
-    for (int j = tid; j < p.Np; j += kTcThreads)
-        s_rows[j] = p.row_map ? __ldg(p.row_map + (long long)b * p.Np + j) : b * p.N_src + j;
-    __syncthreads();
-    // ---- gather Q, K, V head slices: 8 lanes move one 128-byte row
-    {
-        const int chunk = tid & 7;
-        const long long head_off = (long long)h * 64 + chunk * 8;
-        for (int r = tid >> 3; r < q_rows + 2 * p.Np_pad; r += kTcThreads / 8) {
-            int tok, plane;
-            uint32_t dst;
-            if (r < q_rows) { tok = r; plane = 0; dst = s_q + r * 128; }
-            else if (r < q_rows + p.Np_pad) { tok = r - q_rows; plane = 1; dst = s_k + tok * 128; }
-            else { tok = r - q_rows - p.Np_pad; plane = 2; dst = s_v + tok * 128; }
-            const bool ok = tok < p.Np;
-            const long long grow = ok ? (long long)s_rows[tok] : 0;
-            cp_async16_zfill(dst + ((chunk ^ (tok & 7)) << 4), p.qkv + grow * 3 * p.C + plane * p.C + head_off, ok);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        fence_async_smem();                 // cp.async wrote through the generic proxy; UMMA reads through the async proxy
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_mine = (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // units of this CTA
 
-    if (warp == 4) {
-        // ================= MMA issuer =================
+    if (warp >= kAtLoaderWarp0 && p.row_map == nullptr) {
+        // ================= dense loader: the head's tokens are consecutive global rows -> one TMA box per plane =================
+        if (tid == kAtLoaderWarp0 * 32) {
+            tma_prefetch_desc(&tmap_qkv);
+            const uint32_t plane_tx = (uint32_t)p.Np_pad * 128u;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int n = 0; n < n_mine; ++n) {
+                const int u = blockIdx.x + n * gridDim.x;
+                const int nsub = p.two_tiles ? 1 : (unit_item(p, u, 1) >= 0 ? 2 : 1);
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                AT_TRACE(n, 0);
+                mbar_expect_tx(&qk_full[stage], 2u * plane_tx * nsub);
+                mbar_expect_tx(&v_full[stage], plane_tx * nsub);
+                uint8_t* sq = smem_gen + stage * stage_bytes;
+                for (int pl = 0; pl < 3; ++pl)                              // Q, K first (S needs them), then V
+                    for (int t = 0; t < nsub; ++t) {
+                        const int item = unit_item(p, u, t);
+                        const int b = item / p.H, h = item - b * p.H;
+                        // rows past the image's Np belong to the next image (finite values, masked by the softmax)
+                        // or lie past the tensor (zero-filled)
+                        tma_load_2d(sq + pl * p.plane_bytes + t * (128 * 128), &tmap_qkv, pl < 2 ? &qk_full[stage] : &v_full[stage],
+                                    pl * p.C + h * 64, b * p.N_src);
+                    }
+                AT_TRACE(n, 1);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= kAtLoaderWarp0) {
+        // ================= gather loaders: 8 lanes move one token's 128-byte head slice per plane (cp.async) =================
+        // (TMA tile::gather4 does the same gather in hardware but sustains only ~7.5 B/clk/SM on 128-byte rows -
+        //  measured with tools/probes - so the copies are issued as 16-byte cp.async instead.)
+        const int lt = tid - kAtLoaderWarp0 * 32;
+        const int grp = lt >> 3, chunk = lt & 7;
+        const long long C3 = 3LL * p.C;
+        const int nsub = p.two_tiles ? 1 : 2;
+        const int per_sub = p.two_tiles ? 16 : 8;                     // 16-token strides per sub-item (Np_pad <= 256 / 128)
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int n = 0; n < n_mine; ++n) {
+            const int u = blockIdx.x + n * gridDim.x;
+            // global row of every token this lane group moves: all index loads are issued together,
+            // before (and independent of) the wait for the stage to drain
+            int grow[16], hcol[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int item = t < nsub ? unit_item(p, u, t) : -1;
+                const int b = item >= 0 ? item / p.H : 0;
+                hcol[t] = item >= 0 ? (item - b * p.H) * 64 + chunk * 8 : -1;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    // slot t*8+i: second sub-item, or (two_tiles) tokens 128.. of the one head
+                    const int j = grp + (p.two_tiles ? t * 8 + i : i) * (kAtLoaderThreads / 8);
+                    const int it2 = p.two_tiles ? unit_item(p, u, 0) : item;
+                    const int b2 = p.two_tiles ? it2 / p.H : b;
+                    int r = -1;
+                    if (it2 >= 0 && j < p.Np) r = p.row_map ? __ldg(p.row_map + (long long)b2 * p.Np + j) : b2 * p.N_src + j;
+                    grow[t * 8 + i] = r;
+                }
+            }
+            if (p.two_tiles) hcol[1] = hcol[0];
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (lt == 0) AT_TRACE(n, 0);
+            const uint32_t sq = smem_base + stage * stage_bytes, sk = sq + p.plane_bytes, sv = sk + p.plane_bytes;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {                    // pass 0: Q and K (what S needs), pass 1: V
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int t = k >> 3;
+                    const int j = grp + (p.two_tiles ? k : (k & 7)) * (kAtLoaderThreads / 8);
+                    if (hcol[t] < 0 || j >= p.Np_pad || (!p.two_tiles && (k & 7) >= per_sub)) continue;
+                    const bool ok = grow[k] >= 0;
+                    const __nv_bfloat16* src = p.qkv + (long long)(ok ? grow[k] : 0) * C3 + hcol[t];
+                    const int r = (p.two_tiles ? 0 : t * 128) + j;
+                    const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
+                    if (pass == 0) {
+                        if (ok) {
+                            cp_async16(sq + off, src, 16);
+                            cp_async16(sk + off, src + p.C, 16);
+                        }
+                    } else {
+                        cp_async16(sv + off, src + 2 * p.C, ok ? 16 : 0);     // rows past Np are zero-filled: 0 * V must stay 0
+                    }
+                }
+                cp_async_arrive_noinc(pass == 0 ? &qk_full[stage] : &v_full[stage]);
+            }
+            if (lt == 0) AT_TRACE(n, 1);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == kAtMmaWarp) {
+        // ================= MMA issuer: event loop over the two tiles =================
+        // Per tile the tensor pipe runs  S(n) .. [softmax] .. PV(n) S(n+1) .. [softmax] .. ; the two tiles are
+        // out of phase, so the issuer polls (never blocks on) the barrier of whichever tile is ready next.
         if (lane == 0) {
             const uint32_t idesc_s = umma_idesc_bf16(128, p.Np_pad, 0, 0);
             const uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);          // B = V is MN-major
-            for (int qt = 0; qt < p.nqt; ++qt) {
-                const uint32_t ph = qt & 1;
-                if (qt > 0) { mbar_wait(&bar_done, ph ^ 1); tc_fence_after(); }   // previous tile's O has been read
+            const uint32_t kv_stride = p.two_tiles ? 0 : 128 * 128;           // tile 1's K/V rows when a unit holds two heads
+            const int nk = p.Np_pad / 16;
+            // descriptors of stage 0 / tile 0; other stages and tiles are plain adds on the 16-byte address field
+            const uint64_t qd0 = umma_desc_sw128(smem_base, 16, 1024);
+            const uint64_t kd0 = umma_desc_sw128(smem_base + p.plane_bytes, 16, 1024);
+            const uint64_t vd0 = umma_desc_sw128(smem_base + 2 * p.plane_bytes, 16, 1024);
+            int cnt[2] = {n_mine, n_mine};
+            if (unit_item(p, blockIdx.x + (n_mine - 1) * gridDim.x, 1) < 0) cnt[1] = n_mine - 1;
+            int s_next[2] = {0, 0}, pv_next[2] = {0, 0};
+            // stage and phase of the next S / PV of each tile (counters instead of divisions by p.stages)
+            int s_stage[2] = {0, 0}, pv_stage[2] = {0, 0};
+            uint32_t s_phase[2] = {0, 0}, pv_phase[2] = {0, 0};
+            uint32_t pv_cnt = 0;                                              // PVs issued per stage, 4 bits each
+            int qk_seen = 0, v_seen = 0;                                      // units whose Q/K (V) have been seen landed
+            while (pv_next[0] < cnt[0] || pv_next[1] < cnt[1]) {
+                bool did = false;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_base, umma_desc_sw128(s_q + qt * 128 * 128 + k * 32, 16, 1024),
-                              umma_desc_sw128(s_k + k * 32, 16, 1024), idesc_s, k != 0);
-                umma_commit(&bar_s);
-                mbar_wait(&bar_p, ph);                                         // P is in TMEM
-                tc_fence_after();
-                for (int k = 0; k < p.Np_pad / 16; ++k)
-                    umma_bf16_ts(tmem_base + kTcOCol, tmem_base + k * 8,
-                                 umma_desc_sw128(s_v + k * 2048, 16, 1024), idesc_o, k != 0);
-                umma_commit(&bar_o);
+                for (int t = 0; t < 2; ++t) {
+                    const uint32_t tt = tmem_base + t * kAtTileCols;
+                    int n = pv_next[t];
+                    if (n < cnt[t] && s_next[t] > n && mbar_test(&p_full[t], n & 1) &&
+                        (n == 0 || !p.o_outside || mbar_test(&o_empty[t], (n - 1) & 1))) {
+                        // P(n, t) is in TMEM and O(n-1, t) has been read out
+                        const int st = pv_stage[t];
+                        bool ok = true;
+                        if (v_seen <= n) {
+                            if (mbar_test(&v_full[st], pv_phase[t])) v_seen = n + 1;
+                            else ok = false;
+                        }
+                        if (ok) {
+                            tc_fence_after();
+                            AT_TRACE(n, 4 + 4 * t);
+                            const uint64_t vd = vd0 + (uint64_t)((st * stage_bytes + t * kv_stride) >> 4);
+                            for (int k = 0; k < nk; ++k)
+                                umma_bf16_ts(tt + p.o_col, tt + k * 8, vd + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0);
+                            umma_commit(&o_full[t]);
+                            AT_TRACE(n, 5 + 4 * t);
+                            pv_next[t] = n + 1;
+                            if (++pv_stage[t] == p.stages) { pv_stage[t] = 0; pv_phase[t] ^= 1; }
+                            const int tiles_n = (n == n_mine - 1 && cnt[1] < n_mine) ? 1 : 2;
+                            const int sh = st * 4;
+                            pv_cnt += 1u << sh;
+                            if (((pv_cnt >> sh) & 15u) == (uint32_t)tiles_n) {
+                                umma_commit(&empty_bar[st]);                  // the stage may be refilled
+                                pv_cnt &= ~(15u << sh);
+                            }
+                            did = true;
+                        }
+                    }
+                    n = s_next[t];
+                    if (n < cnt[t] && pv_next[t] == n) {                      // PV(n-1, t) is queued: P's columns are free
+                        const int st = s_stage[t];
+                        bool ok = true;
+                        if (qk_seen <= n) {
+                            if (mbar_test(&qk_full[st], s_phase[t])) { qk_seen = n + 1; AT_TRACE(n, 2); }
+                            else ok = false;
+                        }
+                        if (ok && !p.o_outside && n > 0) ok = mbar_test(&o_empty[t], (n - 1) & 1);   // O sits inside S's columns
+                        // stagger the tiles by half a period: tile 1 starts once tile 0 has finished its first softmax, so
+                        // from then on one tile's exp2 pass (MUFU) overlaps the other's PV/S products instead of its exp2 pass
+                        if (ok && t == 1 && n == 0 && cnt[0] > 0) ok = mbar_test(&p_full[0], 0);
+                        if (ok) {
+                            tc_fence_after();
+                            AT_TRACE(n, 6 + 4 * t);
+                            const uint64_t qd = qd0 + (uint64_t)((st * stage_bytes + t * (128 * 128)) >> 4);
+                            const uint64_t kd = kd0 + (uint64_t)((st * stage_bytes + t * kv_stride) >> 4);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(tt, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_s, k != 0);
+                            umma_commit(&s_full[t]);
+                            AT_TRACE(n, 7 + 4 * t);
+                            s_next[t] = n + 1;
+                            if (++s_stage[t] == p.stages) { s_stage[t] = 0; s_phase[t] ^= 1; }
+                            did = true;
+                        }
+                    }
+                }
+                if (!did) __nanosleep(32);
             }
         }
     } else {
         // ================= softmax + epilogue: thread = query row = TMEM lane =================
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int qt = 0; qt < p.nqt; ++qt) {
-            const uint32_t ph = qt & 1;
-            mbar_wait(&bar_s, ph);
+        const int t = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;                               // row inside the tile
+        const uint32_t trow = tmem_base + t * kAtTileCols + ((uint32_t)((warp & 3) * 32) << 16);
+        const int Np = p.Np, Np_pad = p.Np_pad;
+        const float sl2 = p.scale_log2;
+        for (int n = 0; n < n_mine; ++n) {
+            const int item = unit_item(p, blockIdx.x + n * gridDim.x, t);
+            if (item < 0) break;
+            const uint32_t ph = n & 1;
+            const int q = (p.two_tiles ? t * 128 : 0) + row;                   // query index inside the image
+            const bool warp_live = q - lane < Np;                              // any valid row in this warp
+            mbar_wait(&s_full[t], ph);
             tc_fence_after();
-            float mx = -INFINITY;
-            for (int c0 = 0; c0 < p.Np_pad; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(trow + c0, v);
-                tmem_ld_wait();
+            if ((tid & 127) == 0) AT_TRACE(n, 12 + 8 * t);
+            float sum = 1.f;
+            if (warp_live) {
+                uint32_t va[32], vb[32];
+                // ---- pass 1: row maximum, two 32-column loads in flight per wait
+                float mx = -INFINITY;
+                auto max32 = [&](const uint32_t (&cur)[32], int c0) {
+                    if (c0 + 32 <= Np) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c0 + j < p.Np) mx = fmaxf(mx, __uint_as_float(v[j]));
-            }
-            const float mb = mx * p.scale_log2;
-            float sum = 0.f;
-            for (int c0 = 0; c0 < p.Np_pad; c0 += 32) {
-                uint32_t v[32], pk[16];
-                tmem_ld32(trow + c0, v);
-                tmem_ld_wait();
+                        for (int j = 0; j < 32; j += 2) mx = fmax3(mx, __uint_as_float(cur[j]), __uint_as_float(cur[j + 1]));
+                    } else {
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float e0 = (c0 + j < p.Np) ? exp2f(fmaf(__uint_as_float(v[j]), p.scale_log2, -mb)) : 0.f;
-                    float e1 = (c0 + j + 1 < p.Np) ? exp2f(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -mb)) : 0.f;
-                    sum += e0 + e1;
-                    pk[j >> 1] = float2_to_bf16x2(e0, e1);
+                        for (int j = 0; j < 32; ++j) if (c0 + j < Np) mx = fmaxf(mx, __uint_as_float(cur[j]));
+                    }
+                };
+                for (int c0 = 0; c0 < Np; c0 += 64) {
+                    tmem_ld32(trow + c0, va);
+                    if (c0 + 32 < Np) tmem_ld32(trow + c0 + 32, vb);
+                    tmem_ld_wait();
+                    max32(va, c0);
+                    if (c0 + 32 < Np) max32(vb, c0 + 32);
                 }
-                tmem_st16(trow + (c0 >> 1), pk);         // P (bf16 pairs) trails the S columns it overwrites
+                if ((tid & 127) == 0) AT_TRACE(n, 13 + 8 * t);
+                // ---- pass 2: p = exp2((s - max) * scale * log2 e), row sum, bf16 P back into TMEM.
+                // P chunk c lands on columns [16c, 16c+16): always behind the S columns still to be read.
+                const float mb = mx * sl2;
+                sum = 0.f;
+                auto exp_step = [&](const uint32_t (&cur)[32], uint32_t (&nxt)[32], int c0) {
+                    tmem_ld_wait();
+                    if (c0 + 32 < Np_pad) tmem_ld32(trow + c0 + 32, nxt);      // may run <= 16 columns past Np_pad: still this tile's
+                    if (Np_pad - c0 >= 32) {
+                        uint32_t pk[16];
+                        if (c0 + 32 <= Np) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                const float e0 = ex2_approx(fmaf(__uint_as_float(cur[j]), sl2, -mb));
+                                const float e1 = ex2_approx(fmaf(__uint_as_float(cur[j + 1]), sl2, -mb));
+                                sum += e0 + e1;
+                                pk[j >> 1] = float2_to_bf16x2(e0, e1);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                const float e0 = (c0 + j < Np) ? ex2_approx(fmaf(__uint_as_float(cur[j]), sl2, -mb)) : 0.f;
+                                const float e1 = (c0 + j + 1 < Np) ? ex2_approx(fmaf(__uint_as_float(cur[j + 1]), sl2, -mb)) : 0.f;
+                                sum += e0 + e1;
+                                pk[j >> 1] = float2_to_bf16x2(e0, e1);
+                            }
+                        }
+                        tmem_st16(trow + (c0 >> 1), pk);
+                    } else {                                                   // 16-column tail
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            const float e0 = (c0 + j < Np) ? ex2_approx(fmaf(__uint_as_float(cur[j]), sl2, -mb)) : 0.f;
+                            const float e1 = (c0 + j + 1 < Np) ? ex2_approx(fmaf(__uint_as_float(cur[j + 1]), sl2, -mb)) : 0.f;
+                            sum += e0 + e1;
+                            pk[j >> 1] = float2_to_bf16x2(e0, e1);
+                        }
+                        tmem_st8(trow + (c0 >> 1), pk);
+                    }
+                };
+                tmem_ld32(trow, va);
+                for (int c0 = 0; c0 < Np_pad; c0 += 64) {
+                    exp_step(va, vb, c0);
+                    if (c0 + 32 < Np_pad) exp_step(vb, va, c0 + 32);
+                }
+                tmem_st_wait();
             }
-            tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&bar_p);
+            if ((tid & 127) == 0) AT_TRACE(n, 14 + 8 * t);
+            mbar_arrive(&p_full[t]);
             // ---- O = P V done -> normalise, store
-            mbar_wait(&bar_o, ph);
+            mbar_wait(&o_full[t], ph);
             tc_fence_after();
-            const float inv = 1.f / sum;
-            const int q = qt * 128 + warp * 32 + lane;
-            uint32_t o0[32], o1[32];
-            tmem_ld32(trow + kTcOCol, o0);
-            tmem_ld32(trow + kTcOCol + 32, o1);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(&bar_done);
-            if (q < p.Np) {
-                uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)b * p.Np + q) * p.C + h * 64);
+            if ((tid & 127) == 0) AT_TRACE(n, 15 + 8 * t);
+            if (warp_live) {
+                uint32_t o0[32], o1[32];
+                tmem_ld32(trow + p.o_col, o0);
+                tmem_ld32(trow + p.o_col + 32, o1);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&o_empty[t]);
+                if ((tid & 127) == 0) AT_TRACE(n, 16 + 8 * t);
+                if (q < Np) {
+                    const float inv = 1.f / sum;
+                    const int b = item / p.H, h = item - b * p.H;
+                    __nv_bfloat16* dst = p.out + ((long long)b * Np + q) * p.C + h * 64;
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    dst[c] = make_uint4(float2_to_bf16x2(__uint_as_float(o0[8 * c]) * inv, __uint_as_float(o0[8 * c + 1]) * inv),
-                                        float2_to_bf16x2(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv),
-                                        float2_to_bf16x2(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv),
-                                        float2_to_bf16x2(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv));
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t w[8];
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    dst[4 + c] = make_uint4(float2_to_bf16x2(__uint_as_float(o1[8 * c]) * inv, __uint_as_float(o1[8 * c + 1]) * inv),
-                                            float2_to_bf16x2(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv),
-                                            float2_to_bf16x2(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv),
-                                            float2_to_bf16x2(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv));
+                        for (int i = 0; i < 8; ++i)
+                            w[i] = float2_to_bf16x2(__uint_as_float(o0[16 * c + 2 * i]) * inv, __uint_as_float(o0[16 * c + 2 * i + 1]) * inv);
+                        st_global_256(dst + 16 * c, w);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            w[i] = float2_to_bf16x2(__uint_as_float(o1[16 * c + 2 * i]) * inv, __uint_as_float(o1[16 * c + 2 * i + 1]) * inv);
+                        st_global_256(dst + 32 + 16 * c, w);
+                    }
+                }
+                if ((tid & 127) == 0) AT_TRACE(n, 17 + 8 * t);
+            } else {
+                tc_fence_before();
+                mbar_arrive(&o_empty[t]);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kAtMmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTcTmemCols);
+        tmem_dealloc(tmem_base, 512);
     }
+}
+
+int make_tmap_bf16_2d_box(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems,
+                          int box_cols, int box_rows);      // gemm_tcgen05.cu
+
+static int at_num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
 }
 
 // returns 1 if the tcgen05 kernel handled the call, 0 if the shape is outside its range, <0 on error
@@ -184,18 +461,30 @@ int launch_attention_tc(const void* qkv, const int32_t* row_map, void* out, int 
     p.row_map = row_map;
     p.out = static_cast<__nv_bfloat16*>(out);
     p.N_src = N_src; p.Np = Np; p.C = C; p.H = H;
+    p.BH = B * H;
     p.Np_pad = (Np + 15) & ~15;
-    p.nqt = (Np + 127) / 128;
+    p.two_tiles = Np > 128;
+    p.n_units = p.two_tiles ? p.BH : (p.BH + 1) / 2;
     p.scale_log2 = scale * 1.4426950408889634f;
-    const int kv_bytes = (p.Np_pad * 128 + 1023) & ~1023;
-    const int smem = p.nqt * 128 * 128 + 2 * kv_bytes + 1024;
+    p.o_outside = p.Np_pad <= 192;
+    p.o_col = p.o_outside ? 192 : 128;
+    // a plane holds the Q (or K, or V) rows of a stage; tile 1's Q rows / the second head start at row 128
+    const int plane_rows = p.two_tiles ? p.Np_pad : 128 + p.Np_pad;
+    p.plane_bytes = (plane_rows * 128 + 1023) & ~1023;
+    p.stages = kAtSmemBudget / (3 * p.plane_bytes);
+    if (p.stages > kAtMaxStages) p.stages = kAtMaxStages;
+    RAJNI_REQUIRE(p.stages >= 2, RAJNI_EINVAL, "attention_tc: Np=%d leaves room for %d stage(s)", Np, p.stages);
+    const int smem = p.stages * 3 * p.plane_bytes + 256 + 1024;
+    CUtensorMap tmap;
+    if (int rc = make_tmap_bf16_2d_box(&tmap, qkv, (long long)B * N_src, 3LL * C, 3LL * C, 64, p.Np_pad)) return rc;
     static int attr_smem = 0;
     if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "attention_tc: smem attribute: %s", cudaGetErrorString(e));
-        attr_smem = 100 * 1024;
+        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "attention_tc: smem attribute (%d B): %s", smem, cudaGetErrorString(e));
+        attr_smem = smem;
     }
-    attention_tc_kernel<<<dim3(H, B), kTcThreads, smem, stream>>>(p);
+    const int grid = p.n_units < at_num_sms() ? p.n_units : at_num_sms();
+    attention_tc_kernel<<<grid, kAtThreads, smem, stream>>>(tmap, p);
     count_launch();
     int rc = check_launch("attention_tc");
     return rc ? rc : 1;

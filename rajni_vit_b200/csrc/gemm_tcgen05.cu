@@ -363,21 +363,25 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle, zero OOB fill.
-int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols,
-                      long long ld_elems, int box_rows) {
+// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, box_cols], 128-byte swizzle, zero OOB fill.
+int make_tmap_bf16_2d_box(CUtensorMap* map, const void* base, long long rows, long long cols,
+                          long long ld_elems, int box_cols, int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     RAJNI_REQUIRE(fn != nullptr, RAJNI_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
-    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    RAJNI_REQUIRE(r == CUDA_SUCCESS, RAJNI_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%d",
-                  (int)r, rows, cols, ld_elems, box_rows);
+    RAJNI_REQUIRE(r == CUDA_SUCCESS, RAJNI_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d",
+                  (int)r, rows, cols, ld_elems, box_rows, box_cols);
     return 0;
+}
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols,
+                      long long ld_elems, int box_rows) {
+    return make_tmap_bf16_2d_box(map, base, rows, cols, ld_elems, 64, box_rows);
 }
 
 static int num_sms() {

@@ -50,21 +50,27 @@ def gemm_case(name, M, N, K, **kw):
 
 def main():
     B = 256
-    for N in (197, 173, 87):
+    only = set(sys.argv[1:])
+
+    def want(k):
+        return not only or k in only
+
+    for N in (197, 173, 87) if want("gemm") else ():
         M = B * N
         gemm_case(f"qkv N={N}", M, 2304, 768)
         gemm_case(f"proj+res N={N}", M, 768, 768, res=True)
         gemm_case(f"fc1+gelu N={N}", M, 3072, 768, gelu=True)
         gemm_case(f"fc2+res N={N}", M, 768, 3072, res=True)
-    gemm_case("patch-embed", B * 196, 768, 768)
+    if want("gemm"):
+        gemm_case("patch-embed", B * 196, 768, 768)
     # score+select
-    for N, keep in ((197, 172), (173, 151), (152, 120), (121, 86)):
+    for N, keep in ((197, 172), (173, 151), (152, 120), (121, 86)) if want("score") else ():
         qkv = torch.randn(B, N, 2304, device="cuda").bfloat16()
         t = timeit(lambda: ops.score_select(qkv, 12, keep))
         nbytes = B * (2 * N * 768 * 2 + 768 * 2 + 8 * (keep + 1))
         print(f"score_select N={N:3d}            {t*1e6:8.1f} us  {nbytes/t/1e9:7.1f} GB/s ({nbytes/t/1e9/PEAKS['hbm_gbs']*100:5.1f}% of measured HBM)")
     # attention
-    for N, Np in ((197, 197), (197, 173), (173, 152), (152, 121), (121, 87)):
+    for N, Np in ((197, 197), (197, 173), (173, 152), (152, 121), (121, 87), (87, 87)) if want("attn") else ():
         qkv = torch.randn(B * N, 2304, device="cuda").bfloat16()
         rmap = None
         if Np < N:
@@ -74,6 +80,8 @@ def main():
         t = timeit(lambda: ops.attention(qkv, rmap, B, N, Np, 768, 12, 0.125, out=out))
         fl = 4.0 * B * Np * Np * 768
         print(f"attention N={N:3d} Np={Np:3d}        {t*1e6:8.1f} us  {fl/t/1e12:7.1f} TF/s")
+    if not want("rows"):
+        return
     # layernorm
     M = B * 197
     x = torch.randn(M, 768, device="cuda").bfloat16()
