@@ -1,0 +1,160 @@
+"""CPU-side tests (no GPU): host logic of the wrapper, the C-ABI library's exported surface, and the
+data-parallel path of evaluate_model under a world_size-2 gloo group.
+
+No compute entry point of librajni_b200.so is called here - there is no CPU path to call.
+"""
+import ctypes
+import json
+import os
+import re
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from rajni_vit_b200 import _lib                                     # noqa: E402
+from rajni_vit_b200.eval import evaluate_model, shard_bounds         # noqa: E402
+from rajni_vit_b200.wrapper.attention import keep_count             # noqa: E402
+from rajni_vit_b200.wrapper.model import RAJNIViTWrapper, _normalise_schedule   # noqa: E402
+from rajni_vit_b200.vit import create_model                          # noqa: E402
+
+
+# ------------------------------------------------------------------ host arithmetic
+def test_keep_count_matches_python_double_truncation():
+    """rajni/wrapper/attention.py:31-32: max(1, int(keep_ratio * (N - 1))) with Python doubles."""
+    assert keep_count(121, 0.72) == 86          # 0.72 * 120 = 86.39999...
+    assert keep_count(101, 0.29) == 28          # 0.29 * 100 = 28.999999999999996
+    assert keep_count(101, 0.57) == 56
+    assert keep_count(5, 0.01) == 1             # floor of one patch
+    assert keep_count(197, 1.0) == 196
+
+
+@pytest.mark.parametrize("model,sched,expect", [
+    ("C2", {3: .88, 4: .88, 7: .8, 8: .72}, [197, 197, 197, 197, 173, 152, 152, 152, 121, 87, 87, 87]),
+    ("C3", {i: .7 for i in range(3, 12)}, [197, 197, 197, 197, 138, 96, 67, 47, 33, 23, 16, 11]),
+    ("C5", {3: .88, 4: .88, 7: .8, 8: .72}, [577, 577, 577, 577, 507, 446, 446, 446, 357, 257, 257, 257]),
+])
+def test_token_count_trajectories(model, sched, expect):
+    """token counts are shape-determined, so they can be checked without running a kernel."""
+    n = expect[0]
+    got = []
+    for i in range(12):
+        got.append(n)
+        if i in sched:
+            n = keep_count(n, sched[i]) + 1
+    assert got == expect
+
+
+def test_schedule_normalisation():
+    s = _normalise_schedule({"3": {"keep_ratio": 0.5}, 4: {"keep_ratio": 0.9, "update": False}})
+    assert s == {3: {"keep_ratio": 0.5}, 4: {"keep_ratio": 0.9, "update": False}}
+    with pytest.raises(ValueError):
+        _normalise_schedule({"x3": {"keep_ratio": 0.5}})
+    with pytest.raises(KeyError):
+        _normalise_schedule({3: {"update": True}})
+
+
+def test_wrapper_construction_mirrors_reference():
+    """model.py:7-25: blk.attn swapped on scheduled blocks, has_pruner flags, base model aliased as .m / .blocks."""
+    base = create_model("vit_micro_patch16_64", seed=0)
+    w = RAJNIViTWrapper(base, {1: {"keep_ratio": 0.75}, 3: {"keep_ratio": 0.5, "update": False}})
+    assert w.m is base and w.blocks is base.blocks
+    flags = [blk.has_pruner for blk in w.blocks]
+    assert flags == [False, True, False, True]
+    assert type(w.blocks[1].attn).__name__ == "RAJNIAttention"
+    assert w.blocks[3].attn.update is False and w.blocks[3].attn.keep_ratio == 0.5
+    assert w.blocks[1].attn.qkv is not None and w.get_last_stats() is None
+    with pytest.raises(RuntimeError):
+        w(torch.zeros(1, 3, 64, 64))            # CPU tensor: there is no CPU path
+
+
+def test_shard_bounds_partition():
+    for batch in (0, 1, 7, 8, 256, 257):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(batch, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == batch
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+# ------------------------------------------------------------------ the C-ABI library
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rajni_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rajni_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    """include/rajni_b200.h is the contract: every function it declares must be exported by the built library
+    and bound (with a signature) by the ctypes loader."""
+    names = _declared_symbols()
+    assert len(names) >= 10
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in the header but not exported by {_lib.LIB_PATH}"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in rajni_vit_b200/_lib.py"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_library_abi_version_and_error_string():
+    lib = _lib.load()
+    assert lib.rajni_abi_version() == _lib.ABI_VERSION
+    assert isinstance(lib.rajni_last_error(), bytes)
+    assert lib.rajni_launch_count() >= 0
+
+
+def test_library_is_not_linked_against_torch():
+    """The boundary is a plain C ABI: no torch / python symbols are needed to load it."""
+    import subprocess
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "python" not in out and "c10" not in out
+
+
+# ------------------------------------------------------------------ data-parallel evaluate_model (gloo, world 2)
+class _StubModel(torch.nn.Module):
+    """Deterministic stand-in for the wrapper: logits depend only on the image, so every sharding of a
+    batch must give the same predictions."""
+
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.randn(3 * 8 * 8, 10, generator=torch.Generator().manual_seed(3)))
+
+    def forward(self, x):
+        return x.flatten(1) @ self.w
+
+
+def _make_data():
+    g = torch.Generator().manual_seed(11)
+    return [(torch.randn(7, 3, 8, 8, generator=g), torch.randint(0, 10, (7,), generator=g)) for _ in range(3)]
+
+
+def _dp_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        acc, ips = evaluate_model(_StubModel(), _make_data(), device="cpu", warmup=1, progress=False)
+        if rank == 0:
+            json.dump({"acc": acc, "ips": ips}, open(out_path, "w"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_evaluate_model_data_parallel_gloo(tmp_path):
+    """the batch is sharded contiguously by rank and the only collective is the final reduction of
+    (correct, total, images) and MAX(time); a 2-rank run must report the single-process accuracy exactly."""
+    acc1, _ = evaluate_model(_StubModel(), _make_data(), device="cpu", warmup=1, progress=False)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "dp.json")
+    mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+    got = json.load(open(out))
+    assert got["acc"] == pytest.approx(acc1, abs=1e-9)
+    assert got["ips"] > 0
