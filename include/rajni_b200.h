@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RAJNI_ABI_VERSION 1
+#define RAJNI_ABI_VERSION 2
 
 enum {
     RAJNI_OK = 0,
@@ -42,7 +42,9 @@ enum {
     RAJNI_EPI_BIAS = 1,       /* + bias[n]                                       */
     RAJNI_EPI_GELU = 2,       /* exact erf GELU (timm nn.GELU) after bias        */
     RAJNI_EPI_RESIDUAL = 4,   /* + residual[res_row(m), n] after activation      */
-    RAJNI_EPI_OUT_F32 = 8     /* store fp32 instead of bf16                      */
+    RAJNI_EPI_OUT_F32 = 8,    /* store fp32 instead of bf16                      */
+    RAJNI_EPI_LN_FOLD = 16,   /* A is the UN-normalised x; apply LayerNorm algebraically (see below)  */
+    RAJNI_EPI_ROW_STATS = 32  /* also emit per-row partial (sum, sum of squares) of the stored values */
 };
 
 int rajni_abi_version(void);
@@ -94,6 +96,28 @@ int rajni_gemm_bf16(const void* A, const void* W, const float* bias, void* D,
                     const void* residual, long long ldres, const int32_t* res_row_map,
                     long long ldd, const int32_t* out_row_map, void* stream);
 
+/* ---- the same contraction with LayerNorm folded in (model.py:51 norm1 -> qkv, model.py:59 norm2 -> fc1)
+ *
+ *   LN(x) W^T + b  =  rstd[m] * ( x (W.gamma)^T )[m,n]  -  rstd[m]*mean[m] * wsum[n]  +  ( b + W beta )[n]
+ *
+ * so the normalised activations never touch HBM.  Producer side (RAJNI_EPI_ROW_STATS, with the
+ * bias+residual epilogue): for every stored row r the kernel writes, per (n-tile, column half) slot s,
+ * row_stats[s*row_stats_ld + r] = (sum, sum of squares) of the bf16 values it stored in that slot;
+ * rajni_gemm_row_stats_slots(N) is the slot count for an N-column output.  Consumer side
+ * (RAJNI_EPI_LN_FOLD): A = x, W = bf16(W*gamma), bias = b + W beta, ln_wsum[n] = sum_k W'[n,k]; mean and the
+ * biased variance of row m come from summing ln_slots partials at ln_stats[s*ln_stats_ld + m]; K is the
+ * LayerNorm width.  Both need N % tile == 0 and 32-byte aligned rows (true for every ViT width). */
+typedef struct rajni_gemm_args {
+    const void* A; const void* W; const float* bias; void* D;
+    int M, N, K, flags;
+    const void* residual; long long ldres; const int32_t* res_row_map;
+    long long ldd; const int32_t* out_row_map;
+    const float* ln_stats; long long ln_stats_ld; int ln_slots; const float* ln_wsum; float ln_eps;
+    float* row_stats; long long row_stats_ld;
+} rajni_gemm_args;
+int rajni_gemm_bf16_ex(const rajni_gemm_args* args, void* stream);
+int rajni_gemm_row_stats_slots(int N);
+
 /* ---- a4: multi-head attention over kept tokens (attention.py:45-54)
  * qkv [B,N_src,3C] bf16; when row_map != NULL token j of image b is read from
  * global row row_map[b*Np+j] (gather fused into the loads), else N_src == Np.
@@ -104,9 +128,13 @@ int rajni_attention_fwd(const void* qkv, const int32_t* row_map, void* out,
 /* ---- a8: patch-embed front end (model.py:31-37)
  * im2col: images [B,3,S,S] (fp32 if images_f32 else bf16) -> cols [B*P, 3*p*p] bf16
  * in Conv2d weight order (c, ky, kx). Also writes the CLS rows
- * x[b,0,:] = cls_pos0[:] (= cls_token + pos_embed[0], precomputed) into x [B,1+P,C]. */
+ * x[b,0,:] = cls_pos0[:] (= cls_token + pos_embed[0], precomputed) into x [B,1+P,C] and, when
+ * row_stats != NULL, the LayerNorm partials of those rows (slot 0 = (cls_sum, cls_sumsq), the
+ * other `stats_slots-1` slots zero) in the layout RAJNI_EPI_ROW_STATS uses. */
 int rajni_patch_im2col(const void* images, int images_f32, int B, int S, int patch,
-                       void* cols, const void* cls_pos0, void* x, int C, void* stream);
+                       void* cols, const void* cls_pos0, void* x, int C,
+                       float* row_stats, long long row_stats_ld, int stats_slots,
+                       float cls_sum, float cls_sumsq, void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,14 +7,27 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_longlong, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_longlong, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librajni_b200.so")
 
 RAJNI_OK, RAJNI_EINVAL, RAJNI_ECUDA, RAJNI_EARCH, RAJNI_ERANGE = 0, -1, -2, -3, -4
-EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32 = 1, 2, 4, 8
-ABI_VERSION = 1
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32, EPI_LN_FOLD, EPI_ROW_STATS = 1, 2, 4, 8, 16, 32
+ABI_VERSION = 2
+
+
+class GemmArgs(Structure):
+    """struct rajni_gemm_args (include/rajni_b200.h)"""
+    _fields_ = [("A", c_void_p), ("W", c_void_p), ("bias", c_void_p), ("D", c_void_p),
+                ("M", c_int), ("N", c_int), ("K", c_int), ("flags", c_int),
+                ("residual", c_void_p), ("ldres", c_longlong), ("res_row_map", c_void_p),
+                ("ldd", c_longlong), ("out_row_map", c_void_p),
+                ("ln_stats", c_void_p), ("ln_stats_ld", c_longlong), ("ln_slots", c_int),
+                ("ln_wsum", c_void_p), ("ln_eps", c_float),
+                ("row_stats", c_void_p), ("row_stats_ld", c_longlong)]
+
+
 
 # symbol -> (restype, argtypes); mirrors include/rajni_b200.h one to one
 SIGNATURES = {
@@ -30,8 +43,11 @@ SIGNATURES = {
     "rajni_layernorm": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p]),
     "rajni_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p]),
+    "rajni_gemm_bf16_ex": (c_int, [POINTER(GemmArgs), c_void_p]),
+    "rajni_gemm_row_stats_slots": (c_int, [c_int]),
     "rajni_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
-    "rajni_patch_im2col": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "rajni_patch_im2col": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                   c_void_p, c_longlong, c_int, c_float, c_float, c_void_p]),
 }
 
 _lib = None

@@ -8,11 +8,25 @@
 // fc2+residual (model.py:59), patch-embed as a GEMM over im2col'd patches (+pos_embed as the
 // "residual", model.py:34-37) and the classifier head (model.py:66).
 //
-// CTA = 384 threads, one CTA per SM, tiles 128 x BN x 64:
-//   warp 0   : TMA producer (one lane)         warp 1 : tcgen05.mma issuer (one lane)
-//   warp 2   : TMEM allocator                  warp 3 : idle
-//   warps 4-11: epilogue; warp w reads TMEM lanes 32*(w%4).. and column half (w-4)/4
+// CTA = 352 threads, one CTA per SM, tiles 128 x BN x 64:
+//   warps 0-7: epilogue; warp w reads TMEM lanes 32*(w%4).. and column half w/4
+//   warp 8   : TMA producer (one lane)         warp 9 : tcgen05.mma issuer (one lane)
+//   warp 10  : TMEM allocator
+// (the single-lane producer and issuer sit on the HIGHEST warp ids: the issue arbiter favours them over
+//  the epilogue warps they share a scheduler with, so a busy epilogue never delays an MMA or a TMA.)
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue).
+//
+// Epilogue (hot modes): thread = output row (= TMEM lane).  Each warp pulls 32-column chunks of its
+// rows straight from TMEM into registers (next chunk in flight while the current one is processed),
+// applies the fused element-wise work with packed fp32x2 arithmetic (FFMA2), and writes 32-byte
+// pieces of its own row (STG.256) - every thread fills whole sectors, no shared-memory transpose.
+// The accumulator is handed back to the MMA issuer as soon as the last chunk is in registers.
+//
+// LayerNorm folding (model.py:51,59): LN(x) W^T = rstd*(x (W.gamma)^T - mean * wsum) + W beta, so the
+// normalised activations are never materialised: the GEMM that PRODUCES x (proj / fc2 / patch-embed
+// epilogue) also emits per-row partial (sum, sum of squares) of the bf16 values it stores, one slot
+// per (n-tile, column half); the GEMM that CONSUMES LN(x) (qkv / fc1) runs on x itself with
+// gamma-scaled weights and applies  acc*rstd + (-mean*rstd)*wsum[n] + bias'[n]  in its epilogue.
 #include <cuda.h>
 #include <cstdlib>
 
@@ -22,7 +36,8 @@ namespace rajni {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = one 128-byte swizzle row
-constexpr int kGemmThreads = 384;
+constexpr int kGemmThreads = 352;
+constexpr int kTmaWarp = 8, kMmaWarp = 9, kAllocWarp = 10;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiStageBytes = 32 * 128;   // per-warp staging: 32 rows x 32 fp32
 
@@ -49,6 +64,14 @@ struct GemmParams {
     long long ldd, ldres;
     int M, N, K, flags;
     int tiles_m, tiles_n, k_blocks;
+    // LayerNorm folding
+    const float2* ln_stats;     // [ln_slots][ln_stats_ld] partial (sum, sumsq) of the rows of A
+    const float* ln_wsum;       // [N] sum_k W'[n,k]
+    long long ln_stats_ld;
+    int ln_slots;
+    float ln_inv_k, ln_eps;
+    float2* row_stats;          // [tiles_n*2][row_stats_ld] partial (sum, sumsq) of the rows of D, or null
+    long long row_stats_ld;
 };
 
 // Exact-erf GELU (timm nn.GELU) evaluated as x*Phi(x) with
@@ -71,6 +94,28 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return x >= 0.f ? x - s : s;
 }
 
+// Two GELUs per call on packed fp32x2.  Same fit, rearranged so that every step is an FFMA2:
+//   na = -min(|x|, 6),  t = 2^(na*Q(na) - 1) = Phi(-|x|)  (Q = P with odd coefficients negated),
+//   gelu(x) = relu(x) + na * t.      8 FFMA2 + 4 FMNMX + 2 MUFU.EX2 per pair.
+__device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
+    float x0, x1;
+    f2unpack(x2, x0, x1);
+    const uint64_t na = f2pack(fmaxf(-fabsf(x0), -6.0f), fmaxf(-fabsf(x1), -6.0f));
+    uint64_t q = fma2(f2pack(1.339070422545774e-06f, 1.339070422545774e-06f), na,
+                      f2pack(5.1697126764338464e-05f, 5.1697126764338464e-05f));
+    q = fma2(q, na, f2pack(0.0008538772817701101f, 0.0008538772817701101f));
+    q = fma2(q, na, f2pack(0.008219408802688122f, 0.008219408802688122f));
+    q = fma2(q, na, f2pack(0.05341951176524162f, 0.05341951176524162f));
+    q = fma2(q, na, f2pack(-0.45892229676246643f, -0.45892229676246643f));
+    q = fma2(q, na, f2pack(1.1511197090148926f, 1.1511197090148926f));
+    const uint64_t arg = fma2(na, q, f2pack(-1.0f, -1.0f));
+    float a0, a1, t0, t1;
+    f2unpack(arg, a0, a1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+    return fma2(na, f2pack(t0, t1), f2pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+}
+
 // explicit shared-state-space accesses (a generic pointer into dynamic smem compiles to LD.E/ST.E)
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -85,7 +130,7 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // logic (they require N % BN == 0); MODE_GENERIC reads the runtime flags and handles every edge.
 enum { MODE_GENERIC = 0, MODE_BIAS = 1, MODE_BIAS_GELU = 2, MODE_BIAS_RES = 3 };
 
-template <int BN, int CG, int MODE>
+template <int BN, int CG, int MODE, bool LN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
@@ -107,16 +152,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
     const int first_tile = blockIdx.x / CG, tile_stride = gridDim.x / CG;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == kTmaWarp && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == kMmaWarp && lane == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], CG); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps * CG); }
         mbar_fence_init();
     }
-    if (warp == 2) {
+    if (warp == kAllocWarp) {
         if (CG == 2) tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols);
         else tmem_alloc(tmem_slot, Cfg::kTmemCols);
     }
@@ -125,7 +170,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == kTmaWarp) {
         // ================= TMA producer (one lane per CTA) =================
         if (lane == 0) {
             int stage = 0;
@@ -150,7 +195,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ================= MMA issuer (one lane of the leader CTA) =================
         if (lane == 0 && cta_rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, 0, 0);
@@ -184,16 +229,148 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (CG == 2) umma_commit_cg2(&tmem_full[acc], 0x3); else umma_commit(&tmem_full[acc]);
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < kEpiWarps) {
         // ================= epilogue =================
-        const int ew = warp - 4;
+        const int ew = warp;
         const int sub = warp & 3;                   // TMEM sub-partition = warp id % 4
         const int half = ew >> 2;                   // which half of the BN columns
         const uint32_t stg = smem_u32(s_epi + ew * kEpiStageBytes);
-        const bool has_bias = MODE != MODE_GENERIC || (p.flags & RAJNI_EPI_BIAS) != 0;
-        const bool do_gelu = MODE == MODE_BIAS_GELU || (MODE == MODE_GENERIC && (p.flags & RAJNI_EPI_GELU) != 0);
-        const bool has_res = MODE == MODE_BIAS_RES || (MODE == MODE_GENERIC && (p.flags & RAJNI_EPI_RESIDUAL) != 0);
-        const bool out_f32 = MODE == MODE_GENERIC && (p.flags & RAJNI_EPI_OUT_F32) != 0;
+        if (MODE != MODE_GENERIC) {
+            // ---------- hot modes: thread = row, straight from TMEM, packed fp32x2 math, 32-byte row stores ----------
+            constexpr int HALF = BN / 2;                // columns per epilogue warp
+            constexpr int NCH = HALF / 32;              // 32-column chunks per warp and tile
+            constexpr bool kGelu = MODE == MODE_BIAS_GELU;
+            constexpr bool kRes = MODE == MODE_BIAS_RES;
+            const uint32_t sb = stg, sg = stg + HALF * 4;   // this warp's bias / weight-row-sum vectors
+            __nv_bfloat16* const Dp = static_cast<__nv_bfloat16*>(p.D);
+            int local = 0;
+            for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++local) {
+                const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+                const int acc = local & 1;
+                const uint32_t acc_phase = (local >> 1) & 1;
+                const int m = m_blk * (BM * CG) + (int)cta_rank * BM + sub * 32 + lane;
+                const bool valid = m < p.M;
+                const int ncol0 = n_blk * BN + half * HALF;
+                // column vectors of this tile -> the warp's shared slice (read back as broadcasts)
+                __syncwarp();
+                if (lane < HALF / 4) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0) + lane);
+                    sts128(sb + lane * 16, __float_as_uint(bv.x), __float_as_uint(bv.y), __float_as_uint(bv.z), __float_as_uint(bv.w));
+                    if (LN) {
+                        const float4 gv = __ldg(reinterpret_cast<const float4*>(p.ln_wsum + ncol0) + lane);
+                        sts128(sg + lane * 16, __float_as_uint(gv.x), __float_as_uint(gv.y), __float_as_uint(gv.z), __float_as_uint(gv.w));
+                    }
+                }
+                __syncwarp();
+                long long orow = 0;
+                if (valid) orow = p.out_row_map ? (long long)__ldg(p.out_row_map + m) : (long long)m;
+                __nv_bfloat16* const dptr = Dp + orow * p.ldd + ncol0;
+                const __nv_bfloat16* rptr = nullptr;
+                uint32_t rr[2][16];
+                if (kRes) {
+                    if (valid) rptr = p.residual + (p.res_row_map ? (long long)__ldg(p.res_row_map + m) : (long long)m) * p.ldres + ncol0;
+                    if (valid) {
+                        ldg256_nc(rptr, *reinterpret_cast<uint32_t(*)[8]>(&rr[0][0]));
+                        ldg256_nc(rptr + 16, *reinterpret_cast<uint32_t(*)[8]>(&rr[0][8]));
+                    }
+                }
+                uint64_t rstd2 = 0, mr2 = 0;
+                if (LN) {
+                    // row statistics of A from the producer's partial sums (model.py:51,59: LayerNorm, biased variance)
+                    float s1 = 0.f, s2 = 0.f;
+                    if (valid) {
+                        for (int sl = 0; sl < p.ln_slots; ++sl) {
+                            const float2 t = __ldg(p.ln_stats + (long long)sl * p.ln_stats_ld + m);
+                            s1 += t.x;
+                            s2 += t.y;
+                        }
+                    }
+                    const float mean = s1 * p.ln_inv_k;
+                    const float rstd = rsqrtf(fmaxf(s2 * p.ln_inv_k - mean * mean, 0.f) + p.ln_eps);
+                    rstd2 = f2pack(rstd, rstd);
+                    mr2 = f2pack(-mean * rstd, -mean * rstd);
+                }
+                uint64_t sum2 = 0, sq2 = 0;                  // (0.f, 0.f)
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
+                uint32_t va[32], vb[32];
+                tmem_ld32(taddr, va);
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    uint32_t (&cur)[32] = (ch & 1) ? vb : va;
+                    uint32_t (&nxt)[32] = (ch & 1) ? va : vb;
+                    tmem_ld_wait();
+                    if (ch + 1 < NCH) {
+                        tmem_ld32(taddr + (ch + 1) * 32, nxt);
+                    } else {
+                        // every chunk of this warp's rows is in registers: give the accumulator back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+                            else mbar_arrive(&tmem_empty[acc]);
+                        }
+                    }
+                    if (kRes && ch + 1 < NCH && valid) {
+                        ldg256_nc(rptr + (ch + 1) * 32, *reinterpret_cast<uint32_t(*)[8]>(&rr[(ch + 1) & 1][0]));
+                        ldg256_nc(rptr + (ch + 1) * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rr[(ch + 1) & 1][8]));
+                    }
+                    uint32_t o[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bv = lds128(sb + (ch * 32 + j) * 4);
+                        uint64_t x01 = f2pack(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1]));
+                        uint64_t x23 = f2pack(__uint_as_float(cur[j + 2]), __uint_as_float(cur[j + 3]));
+                        if (LN) {
+                            const float4 gv = lds128(sg + (ch * 32 + j) * 4);
+                            x01 = fma2(x01, rstd2, fma2(mr2, f2pack(gv.x, gv.y), f2pack(bv.x, bv.y)));
+                            x23 = fma2(x23, rstd2, fma2(mr2, f2pack(gv.z, gv.w), f2pack(bv.z, bv.w)));
+                        } else {
+                            x01 = add2(x01, f2pack(bv.x, bv.y));
+                            x23 = add2(x23, f2pack(bv.z, bv.w));
+                        }
+                        if (kGelu) {
+                            x01 = gelu_erf2(x01);
+                            x23 = gelu_erf2(x23);
+                        }
+                        if (kRes) {
+                            const float2 r0 = bf16x2_to_float2(rr[ch & 1][j >> 1]), r1 = bf16x2_to_float2(rr[ch & 1][(j >> 1) + 1]);
+                            x01 = add2(x01, f2pack(r0.x, r0.y));
+                            x23 = add2(x23, f2pack(r1.x, r1.y));
+                        }
+                        float e0, e1, e2, e3;
+                        f2unpack(x01, e0, e1);
+                        f2unpack(x23, e2, e3);
+                        o[j >> 1] = float2_to_bf16x2(e0, e1);
+                        o[(j >> 1) + 1] = float2_to_bf16x2(e2, e3);
+                        if (kRes) {
+                            // statistics of the values as stored (bf16-rounded), for the LayerNorm that follows
+                            const float2 q0 = bf16x2_to_float2(o[j >> 1]), q1 = bf16x2_to_float2(o[(j >> 1) + 1]);
+                            const uint64_t y01 = f2pack(q0.x, q0.y), y23 = f2pack(q1.x, q1.y);
+                            sum2 = add2(sum2, add2(y01, y23));
+                            sq2 = fma2(y01, y01, sq2);
+                            sq2 = fma2(y23, y23, sq2);
+                        }
+                    }
+                    if (valid) {
+                        stg256(dptr + ch * 32, *reinterpret_cast<uint32_t(*)[8]>(&o[0]));
+                        stg256(dptr + ch * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&o[8]));
+                    }
+                }
+                if (kRes && p.row_stats != nullptr && valid) {
+                    float a0, a1, b0, b1;
+                    f2unpack(sum2, a0, a1);
+                    f2unpack(sq2, b0, b1);
+                    p.row_stats[(long long)(n_blk * 2 + half) * p.row_stats_ld + orow] = make_float2(a0 + a1, b0 + b1);
+                }
+            }
+        } else {
+        // ---------- generic mode: runtime flags, column tails, fp32 output, staged through shared memory ----------
+        const bool has_bias = (p.flags & RAJNI_EPI_BIAS) != 0;
+        const bool do_gelu = (p.flags & RAJNI_EPI_GELU) != 0;
+        const bool has_res = (p.flags & RAJNI_EPI_RESIDUAL) != 0;
+        const bool out_f32 = (p.flags & RAJNI_EPI_OUT_F32) != 0;
         const int r_in = lane >> 3;                 // row within a group of 4 (phase 2)
         const int c4 = lane & 7;                    // 4-column group within the 32-column chunk
         // phase-1 / phase-2 staging addresses (XOR swizzle on 16-byte slots; both conflict-free)
@@ -227,107 +404,66 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         roff[it] = (p.res_row_map ? (long long)__ldg(p.res_row_map + m) : (long long)m) * p.ldres + ncol0;
                 }
             }
-            // pull this warp's residual slab towards L2 while the MMAs of this tile are still running
-            if (has_res) {
-#pragma unroll
-                for (int it = 0; it < 8; ++it)
-                    if ((valid >> it) & 1) prefetch_l2(p.residual + roff[it] - c4 * 4 + c4 * (BN / 16));
-            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
             for (int ch = 0; ch < BN / 64; ++ch) {
                 const int n = ncol0 + ch * 32;
                 const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2) + ch * 32);
-                if (MODE != MODE_GENERIC) {
-                    // ---------- hot path: no column tails, flags known at compile time ----------
-                    uint2 rres[8];
-                    if (MODE == MODE_BIAS_RES) {
+                // ---------- generic path: runtime flags, column tails, fp32 output ----------
+                const bool full4 = (n + 4 <= p.N);
+                uint32_t v[32];
+                tmem_ld32(taddr, v);
+                tmem_ld_wait();
 #pragma unroll
-                        for (int it = 0; it < 8; ++it)
-                            rres[it] = ((valid >> it) & 1) ? __ldg(reinterpret_cast<const uint2*>(p.residual + roff[it] + ch * 32))
-                                                           : make_uint2(0u, 0u);
+                for (int c = 0; c < 8; ++c) sts128(st_addr[c], v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                __syncwarp();
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_bias && n < p.N) {
+                    if (full4) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                    else {
+                        bv.x = __ldg(p.bias + n);
+                        if (n + 1 < p.N) bv.y = __ldg(p.bias + n + 1);
+                        if (n + 2 < p.N) bv.z = __ldg(p.bias + n + 2);
                     }
-                    const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                    uint32_t v[32];
-                    tmem_ld32(taddr, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) sts128(st_addr[c], v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                    __syncwarp();
-                    float4 a[8];
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) a[it] = lds128(ld_addr[it]);
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        float4 t = a[it];
-                        t.x += bv.x; t.y += bv.y; t.z += bv.z; t.w += bv.w;
-                        if (MODE == MODE_BIAS_GELU) { t.x = gelu_erf(t.x); t.y = gelu_erf(t.y); t.z = gelu_erf(t.z); t.w = gelu_erf(t.w); }
-                        if (MODE == MODE_BIAS_RES) {
-                            const float2 r0 = bf16x2_to_float2(rres[it].x), r1 = bf16x2_to_float2(rres[it].y);
-                            t.x += r0.x; t.y += r0.y; t.z += r1.x; t.w += r1.y;
-                        }
-                        if ((valid >> it) & 1)
-                            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.D) + ooff[it] + ch * 32) =
-                                make_uint2(float2_to_bf16x2(t.x, t.y), float2_to_bf16x2(t.z, t.w));
-                    }
-                    __syncwarp();           // staging is overwritten by the next chunk
-                } else {
-                    // ---------- generic path: runtime flags, column tails, fp32 output ----------
-                    const bool full4 = (n + 4 <= p.N);
-                    uint32_t v[32];
-                    tmem_ld32(taddr, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) sts128(st_addr[c], v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                    __syncwarp();
-                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (has_bias && n < p.N) {
-                        if (full4) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                        else {
-                            bv.x = __ldg(p.bias + n);
-                            if (n + 1 < p.N) bv.y = __ldg(p.bias + n + 1);
-                            if (n + 2 < p.N) bv.z = __ldg(p.bias + n + 2);
-                        }
-                    }
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        float4 a = lds128(ld_addr[it]);
-                        if (!((valid >> it) & 1) || n >= p.N) continue;
-                        a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
-                        if (do_gelu) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
-                        if (has_res) {
-                            const __nv_bfloat16* rp = p.residual + roff[it] + ch * 32;
-                            if (full4) {
-                                const uint2 rr = __ldg(reinterpret_cast<const uint2*>(rp));
-                                const float2 r0 = bf16x2_to_float2(rr.x), r1 = bf16x2_to_float2(rr.y);
-                                a.x += r0.x; a.y += r0.y; a.z += r1.x; a.w += r1.y;
-                            } else {
-                                a.x += __bfloat162float(rp[0]);
-                                if (n + 1 < p.N) a.y += __bfloat162float(rp[1]);
-                                if (n + 2 < p.N) a.z += __bfloat162float(rp[2]);
-                            }
-                        }
-                        if (out_f32) {
-                            float* dp = static_cast<float*>(p.D) + ooff[it] + ch * 32;
-                            if (full4) *reinterpret_cast<float4*>(dp) = a;
-                            else {
-                                dp[0] = a.x;
-                                if (n + 1 < p.N) dp[1] = a.y;
-                                if (n + 2 < p.N) dp[2] = a.z;
-                            }
-                        } else {
-                            __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(p.D) + ooff[it] + ch * 32;
-                            if (full4) *reinterpret_cast<uint2*>(dp) = make_uint2(float2_to_bf16x2(a.x, a.y), float2_to_bf16x2(a.z, a.w));
-                            else {
-                                dp[0] = __float2bfloat16(a.x);
-                                if (n + 1 < p.N) dp[1] = __float2bfloat16(a.y);
-                                if (n + 2 < p.N) dp[2] = __float2bfloat16(a.z);
-                            }
-                        }
-                    }
-                    __syncwarp();
                 }
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    float4 a = lds128(ld_addr[it]);
+                    if (!((valid >> it) & 1) || n >= p.N) continue;
+                    a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
+                    if (do_gelu) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+                    if (has_res) {
+                        const __nv_bfloat16* rp = p.residual + roff[it] + ch * 32;
+                        if (full4) {
+                            const uint2 rr = __ldg(reinterpret_cast<const uint2*>(rp));
+                            const float2 r0 = bf16x2_to_float2(rr.x), r1 = bf16x2_to_float2(rr.y);
+                            a.x += r0.x; a.y += r0.y; a.z += r1.x; a.w += r1.y;
+                        } else {
+                            a.x += __bfloat162float(rp[0]);
+                            if (n + 1 < p.N) a.y += __bfloat162float(rp[1]);
+                            if (n + 2 < p.N) a.z += __bfloat162float(rp[2]);
+                        }
+                    }
+                    if (out_f32) {
+                        float* dp = static_cast<float*>(p.D) + ooff[it] + ch * 32;
+                        if (full4) *reinterpret_cast<float4*>(dp) = a;
+                        else {
+                            dp[0] = a.x;
+                            if (n + 1 < p.N) dp[1] = a.y;
+                            if (n + 2 < p.N) dp[2] = a.z;
+                        }
+                    } else {
+                        __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(p.D) + ooff[it] + ch * 32;
+                        if (full4) *reinterpret_cast<uint2*>(dp) = make_uint2(float2_to_bf16x2(a.x, a.y), float2_to_bf16x2(a.z, a.w));
+                        else {
+                            dp[0] = __float2bfloat16(a.x);
+                            if (n + 1 < p.N) dp[1] = __float2bfloat16(a.y);
+                            if (n + 2 < p.N) dp[2] = __float2bfloat16(a.z);
+                        }
+                    }
+                }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -336,11 +472,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 else mbar_arrive(&tmem_empty[acc]);
             }
         }
+        }
     }
 
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
-    if (warp == 2) {
+    if (warp == kAllocWarp) {
         tc_fence_after();
         if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
         else tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -395,7 +532,7 @@ static int num_sms() {
     return n;
 }
 
-template <int BN, int CG, int MODE>
+template <int BN, int CG, int MODE, bool LN>
 static int launch_gemm_mode(const void* A, const void* W, GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, CG>;
     CUtensorMap ta, tb;
@@ -406,7 +543,7 @@ static int launch_gemm_mode(const void* A, const void* W, GemmParams& p, cudaStr
     p.k_blocks = (p.K + BK - 1) / BK;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG, MODE, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "gemm: smem attribute (%d B): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
         attr_done = true;
     }
@@ -425,57 +562,109 @@ static int launch_gemm_mode(const void* A, const void* W, GemmParams& p, cudaStr
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG, MODE>, ta, tb, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG, MODE, LN>, ta, tb, p);
     count_launch();
     RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "gemm_bf16: launch failed: %s", cudaGetErrorString(e));
     return check_launch("gemm_bf16");
 }
 
-// pick the compile-time epilogue when the problem has no column tail and a hot flag combination
+static bool aligned32(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 31u) == 0; }
+
+// Pick the compile-time epilogue.  The hot modes need: no column tail, 32-byte-aligned rows of D (and of
+// the residual), bf16 output, and one of the flag combinations below; everything else runs MODE_GENERIC.
 template <int BN, int CG>
 static int launch_gemm(const void* A, const void* W, GemmParams& p, cudaStream_t stream) {
-    if (p.N % BN == 0) {
-        switch (p.flags) {
-            case RAJNI_EPI_BIAS: return launch_gemm_mode<BN, CG, MODE_BIAS>(A, W, p, stream);
-            case RAJNI_EPI_BIAS | RAJNI_EPI_GELU: return launch_gemm_mode<BN, CG, MODE_BIAS_GELU>(A, W, p, stream);
-            case RAJNI_EPI_BIAS | RAJNI_EPI_RESIDUAL: return launch_gemm_mode<BN, CG, MODE_BIAS_RES>(A, W, p, stream);
-            default: break;
-        }
+    const int ln = p.flags & RAJNI_EPI_LN_FOLD, stats = p.flags & RAJNI_EPI_ROW_STATS;
+    const int core = p.flags & ~(RAJNI_EPI_LN_FOLD | RAJNI_EPI_ROW_STATS);
+    bool hot = p.N % BN == 0 && p.ldd % 16 == 0 && aligned32(p.D);
+    if (core & RAJNI_EPI_RESIDUAL) hot = hot && p.ldres % 16 == 0 && aligned32(p.residual);
+    if (hot) {
+        if (core == RAJNI_EPI_BIAS && !stats)
+            return ln ? launch_gemm_mode<BN, CG, MODE_BIAS, true>(A, W, p, stream) : launch_gemm_mode<BN, CG, MODE_BIAS, false>(A, W, p, stream);
+        if (core == (RAJNI_EPI_BIAS | RAJNI_EPI_GELU) && !stats)
+            return ln ? launch_gemm_mode<BN, CG, MODE_BIAS_GELU, true>(A, W, p, stream) : launch_gemm_mode<BN, CG, MODE_BIAS_GELU, false>(A, W, p, stream);
+        if (core == (RAJNI_EPI_BIAS | RAJNI_EPI_RESIDUAL) && !ln)
+            return launch_gemm_mode<BN, CG, MODE_BIAS_RES, false>(A, W, p, stream);
     }
-    return launch_gemm_mode<BN, CG, MODE_GENERIC>(A, W, p, stream);
+    RAJNI_REQUIRE(!ln && !stats, RAJNI_EINVAL,
+                  "rajni_gemm_bf16: LN_FOLD / ROW_STATS need N %% %d == 0, ldd/ldres multiples of 16 and 32-byte aligned rows "
+                  "(N=%d ldd=%lld ldres=%lld flags=%d)", BN, p.N, p.ldd, p.ldres, p.flags);
+    return launch_gemm_mode<BN, CG, MODE_GENERIC, false>(A, W, p, stream);
+}
+
+// tile width: minimise padded columns; the 64-wide tile runs at ~2/3 rate (shared-memory bound).
+// `exact` (LN_FOLD / ROW_STATS epilogues, which have no column-tail path): the widest tile that divides N.
+static int pick_bn(int N, bool exact) {
+    if (exact) return N % 256 == 0 ? 256 : N % 128 == 0 ? 128 : 64;
+    auto cost = [&](int bn) { long long padded = (long long)((N + bn - 1) / bn) * bn; return bn == 64 ? padded * 3 / 2 : padded; };
+    int bn = 256;
+    if (cost(128) < cost(bn)) bn = 128;
+    if (cost(64) < cost(bn)) bn = 64;
+    return bn;
 }
 
 }  // namespace rajni
 
 using namespace rajni;
 
-extern "C" int rajni_gemm_bf16(const void* A, const void* W, const float* bias, void* D,
-                               int M, int N, int K, int flags,
-                               const void* residual, long long ldres, const int32_t* res_row_map,
-                               long long ldd, const int32_t* out_row_map, void* stream) {
-    RAJNI_REQUIRE(A && W && D, RAJNI_EINVAL, "rajni_gemm_bf16: null pointer");
+extern "C" int rajni_gemm_row_stats_slots(int N) {
+    if (N <= 0) return 0;
+    if (N % 64 != 0) return 0;                      // ROW_STATS needs whole tiles
+    return 2 * (N / pick_bn(N, true));
+}
+
+extern "C" int rajni_gemm_bf16_ex(const rajni_gemm_args* a, void* stream) {
+    RAJNI_REQUIRE(a != nullptr, RAJNI_EINVAL, "rajni_gemm_bf16_ex: null argument block");
+    const int M = a->M, N = a->N, K = a->K, flags = a->flags;
+    RAJNI_REQUIRE(a->A && a->W && a->D, RAJNI_EINVAL, "rajni_gemm_bf16: null pointer");
     RAJNI_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0, RAJNI_EINVAL, "rajni_gemm_bf16: M=%d N=%d K=%d (K must be a multiple of 8)", M, N, K);
-    RAJNI_REQUIRE(!(flags & RAJNI_EPI_BIAS) || bias, RAJNI_EINVAL, "rajni_gemm_bf16: bias flag without bias");
-    RAJNI_REQUIRE(!(flags & RAJNI_EPI_RESIDUAL) || residual, RAJNI_EINVAL, "rajni_gemm_bf16: residual flag without residual");
-    RAJNI_REQUIRE(ldd >= N && ldd % 4 == 0 && (!(flags & RAJNI_EPI_RESIDUAL) || ldres % 4 == 0), RAJNI_EINVAL,
-                  "rajni_gemm_bf16: ldd=%lld ldres=%lld must be multiples of 4 and ldd >= N", ldd, ldres);
+    RAJNI_REQUIRE(!(flags & RAJNI_EPI_BIAS) || a->bias, RAJNI_EINVAL, "rajni_gemm_bf16: bias flag without bias");
+    RAJNI_REQUIRE(!(flags & RAJNI_EPI_RESIDUAL) || a->residual, RAJNI_EINVAL, "rajni_gemm_bf16: residual flag without residual");
+    RAJNI_REQUIRE(a->ldd >= N && a->ldd % 4 == 0 && (!(flags & RAJNI_EPI_RESIDUAL) || a->ldres % 4 == 0), RAJNI_EINVAL,
+                  "rajni_gemm_bf16: ldd=%lld ldres=%lld must be multiples of 4 and ldd >= N", a->ldd, a->ldres);
+    if (flags & RAJNI_EPI_LN_FOLD)
+        RAJNI_REQUIRE(a->ln_stats && a->ln_wsum && a->ln_slots > 0 && a->ln_stats_ld >= M && (flags & RAJNI_EPI_BIAS) && !(flags & RAJNI_EPI_OUT_F32),
+                      RAJNI_EINVAL, "rajni_gemm_bf16: LN_FOLD needs ln_stats, ln_wsum, ln_slots > 0, ln_stats_ld >= M, a bias and bf16 output");
+    if (flags & RAJNI_EPI_ROW_STATS)
+        RAJNI_REQUIRE(a->row_stats && a->row_stats_ld > 0 && (flags & RAJNI_EPI_RESIDUAL) && !(flags & RAJNI_EPI_OUT_F32), RAJNI_EINVAL,
+                      "rajni_gemm_bf16: ROW_STATS needs row_stats, row_stats_ld and the bias+residual bf16 epilogue");
     GemmParams p{};
-    p.bias = bias; p.D = D;
-    p.residual = static_cast<const __nv_bfloat16*>(residual);
-    p.res_row_map = res_row_map; p.out_row_map = out_row_map;
-    p.ldd = ldd; p.ldres = ldres;
+    p.bias = a->bias; p.D = a->D;
+    p.residual = static_cast<const __nv_bfloat16*>(a->residual);
+    p.res_row_map = a->res_row_map; p.out_row_map = a->out_row_map;
+    p.ldd = a->ldd; p.ldres = a->ldres;
     p.M = M; p.N = N; p.K = K; p.flags = flags;
-    // tile width: minimise padded columns; the 64-wide tile runs at ~2/3 rate (shared-memory bound)
-    auto cost = [&](int bn) { long long padded = (long long)((N + bn - 1) / bn) * bn; return bn == 64 ? padded * 3 / 2 : padded; };
-    int bn = 256;
-    if (cost(128) < cost(bn)) bn = 128;
-    if (cost(64) < cost(bn)) bn = 64;
+    p.ln_stats = reinterpret_cast<const float2*>(a->ln_stats);
+    p.ln_wsum = a->ln_wsum;
+    p.ln_stats_ld = a->ln_stats_ld;
+    p.ln_slots = a->ln_slots;
+    p.ln_inv_k = 1.0f / (float)K;
+    p.ln_eps = a->ln_eps;
+    p.row_stats = (flags & RAJNI_EPI_ROW_STATS) ? reinterpret_cast<float2*>(a->row_stats) : nullptr;
+    p.row_stats_ld = a->row_stats_ld;
+    const bool exact = (flags & (RAJNI_EPI_LN_FOLD | RAJNI_EPI_ROW_STATS)) != 0;
+    RAJNI_REQUIRE(!exact || N % 64 == 0, RAJNI_EINVAL, "rajni_gemm_bf16: LN_FOLD / ROW_STATS need N %% 64 == 0 (N=%d)", N);
+    const int bn = pick_bn(N, exact);
     auto s = static_cast<cudaStream_t>(stream);
     // wide problems run as CTA pairs (256 x 256 tiles); narrow ones keep single-CTA tiles
     static const bool force_cg1 = getenv("RAJNI_GEMM_CG1") != nullptr;     // debugging aid
     switch (bn) {
-        case 256: return (M > BM && !force_cg1) ? launch_gemm<256, 2>(A, W, p, s) : launch_gemm<256, 1>(A, W, p, s);
-        case 128: return launch_gemm<128, 1>(A, W, p, s);
-        default: return launch_gemm<64, 1>(A, W, p, s);
+        case 256: return (M > BM && !force_cg1) ? launch_gemm<256, 2>(a->A, a->W, p, s) : launch_gemm<256, 1>(a->A, a->W, p, s);
+        case 128: return launch_gemm<128, 1>(a->A, a->W, p, s);
+        default: return launch_gemm<64, 1>(a->A, a->W, p, s);
     }
+}
+
+extern "C" int rajni_gemm_bf16(const void* A, const void* W, const float* bias, void* D,
+                               int M, int N, int K, int flags,
+                               const void* residual, long long ldres, const int32_t* res_row_map,
+                               long long ldd, const int32_t* out_row_map, void* stream) {
+    RAJNI_REQUIRE(!(flags & (RAJNI_EPI_LN_FOLD | RAJNI_EPI_ROW_STATS)), RAJNI_EINVAL,
+                  "rajni_gemm_bf16: LN_FOLD / ROW_STATS need rajni_gemm_bf16_ex");
+    rajni_gemm_args a{};
+    a.A = A; a.W = W; a.bias = bias; a.D = D;
+    a.M = M; a.N = N; a.K = K; a.flags = flags;
+    a.residual = residual; a.ldres = ldres; a.res_row_map = res_row_map;
+    a.ldd = ldd; a.out_row_map = out_row_map;
+    return rajni_gemm_bf16_ex(&a, stream);
 }

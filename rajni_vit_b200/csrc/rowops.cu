@@ -99,7 +99,9 @@ template <bool F32>
 __global__ void __launch_bounds__(256) im2col16_kernel(const void* __restrict__ images, int B, int S,
                                                        __nv_bfloat16* __restrict__ cols,
                                                        const uint4* __restrict__ cls_pos0,
-                                                       uint4* __restrict__ x, int C) {
+                                                       uint4* __restrict__ x, int C,
+                                                       float2* __restrict__ row_stats, long long stats_ld, int stats_slots,
+                                                       float cls_sum, float cls_sumsq) {
     const int G = S >> 4;                       // patches per side
     const long long strips = (long long)B * G * 3 * 16 * G;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -135,6 +137,13 @@ __global__ void __launch_bounds__(256) im2col16_kernel(const void* __restrict__ 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * cchunks; i += stride) {
         int b = (int)(i / cchunks), j = (int)(i % cchunks);
         x[(long long)b * P1 * cchunks + j] = __ldg(cls_pos0 + j);
+    }
+    // LayerNorm partials of the CLS rows (the patch rows' partials come from the embed GEMM's epilogue)
+    if (row_stats != nullptr) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * stats_slots; i += stride) {
+            int b = (int)(i / stats_slots), s = (int)(i % stats_slots);
+            row_stats[(long long)s * stats_ld + (long long)b * P1] = s == 0 ? make_float2(cls_sum, cls_sumsq) : make_float2(0.f, 0.f);
+        }
     }
 }
 
@@ -180,10 +189,14 @@ extern "C" int rajni_layernorm(const void* x, long long in_row_stride, const flo
 }
 
 extern "C" int rajni_patch_im2col(const void* images, int images_f32, int B, int S, int patch,
-                                  void* cols, const void* cls_pos0, void* x, int C, void* stream) {
+                                  void* cols, const void* cls_pos0, void* x, int C,
+                                  float* row_stats, long long row_stats_ld, int stats_slots,
+                                  float cls_sum, float cls_sumsq, void* stream) {
     RAJNI_REQUIRE(images && cols && cls_pos0 && x, RAJNI_EINVAL, "rajni_patch_im2col: null pointer");
     RAJNI_REQUIRE(patch == 16 && S > 0 && S % 16 == 0 && B > 0 && C % 8 == 0, RAJNI_EINVAL,
                   "rajni_patch_im2col: patch=%d S=%d B=%d C=%d unsupported (patch must be 16)", patch, S, B, C);
+    RAJNI_REQUIRE(row_stats == nullptr || (stats_slots > 0 && row_stats_ld >= (long long)B * ((S / 16) * (S / 16) + 1)), RAJNI_EINVAL,
+                  "rajni_patch_im2col: row_stats needs stats_slots > 0 and row_stats_ld >= B*(P+1)");
     const int G = S / 16;
     const long long strips = (long long)B * G * 3 * 16 * G;
     long long blocks = (strips + 255) / 256;
@@ -191,10 +204,12 @@ extern "C" int rajni_patch_im2col(const void* images, int images_f32, int B, int
     auto s = static_cast<cudaStream_t>(stream);
     if (images_f32)
         im2col16_kernel<true><<<(int)blocks, 256, 0, s>>>(images, B, S, static_cast<__nv_bfloat16*>(cols),
-                                                          static_cast<const uint4*>(cls_pos0), static_cast<uint4*>(x), C);
+                                                          static_cast<const uint4*>(cls_pos0), static_cast<uint4*>(x), C,
+                                                          reinterpret_cast<float2*>(row_stats), row_stats_ld, stats_slots, cls_sum, cls_sumsq);
     else
         im2col16_kernel<false><<<(int)blocks, 256, 0, s>>>(images, B, S, static_cast<__nv_bfloat16*>(cols),
-                                                           static_cast<const uint4*>(cls_pos0), static_cast<uint4*>(x), C);
+                                                           static_cast<const uint4*>(cls_pos0), static_cast<uint4*>(x), C,
+                                                           reinterpret_cast<float2*>(row_stats), row_stats_ld, stats_slots, cls_sum, cls_sumsq);
     count_launch();
     return check_launch("patch_im2col");
 }

@@ -8,7 +8,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import EPI_BIAS, EPI_GELU, EPI_OUT_F32, EPI_RESIDUAL  # noqa: F401  (re-exported)
+from ._lib import EPI_BIAS, EPI_GELU, EPI_LN_FOLD, EPI_OUT_F32, EPI_RESIDUAL, EPI_ROW_STATS  # noqa: F401  (re-exported)
 
 _checked_devices = set()
 _prof = None        # list of (name, work, start_event, end_event) while profile_steps() runs
@@ -136,20 +136,37 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
+def row_stats_slots(n_cols: int) -> int:
+    """Partial-sum slots per row that a ``row_stats`` GEMM with ``n_cols`` output columns writes."""
+    return int(_lib.load().rajni_gemm_row_stats_slots(n_cols))
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], M: int, N: int, K: int, *,
          gelu: bool = False, residual: Optional[torch.Tensor] = None, ldres: Optional[int] = None,
          res_row_map: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-         ldd: Optional[int] = None, out_row_map: Optional[torch.Tensor] = None, out_f32: bool = False
-         ) -> torch.Tensor:
-    """out[orow(m), n] = epi(sum_k a[m,k] w[n,k]); a [M,K] bf16, w [N,K] bf16, bias fp32 [N]."""
+         ldd: Optional[int] = None, out_row_map: Optional[torch.Tensor] = None, out_f32: bool = False,
+         ln: Optional[tuple] = None, row_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[orow(m), n] = epi(sum_k a[m,k] w[n,k]); a [M,K] bf16, w [N,K] bf16, bias fp32 [N].
+
+    ``ln = (stats, slots, wsum, eps)``: LayerNorm folded in (a is the un-normalised x, w = W*gamma,
+    bias = b + W beta, wsum[n] = sum_k w[n,k], stats fp32 [>=slots, rows, 2] partial sums of x's rows).
+    ``row_stats`` fp32 [slots, rows, 2]: also emit the partial sums of the rows this GEMM stores."""
     flags = (EPI_BIAS if bias is not None else 0) | (EPI_GELU if gelu else 0) | \
             (EPI_RESIDUAL if residual is not None else 0) | (EPI_OUT_F32 if out_f32 else 0)
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
-    _call("gemm", 2.0 * M * N * K, _lib.load().rajni_gemm_bf16,
-          a.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, flags,
-          _ptr(residual), (N if ldres is None else ldres), _ptr(res_row_map),
-          (N if ldd is None else ldd), _ptr(out_row_map), _stream(a))
+    args = _lib.GemmArgs(a.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, flags,
+                         _ptr(residual), (N if ldres is None else ldres), _ptr(res_row_map),
+                         (N if ldd is None else ldd), _ptr(out_row_map))
+    if ln is not None:
+        stats, slots, wsum, eps = ln
+        args.flags |= EPI_LN_FOLD
+        args.ln_stats, args.ln_stats_ld, args.ln_slots = stats.data_ptr(), stats.shape[1], slots
+        args.ln_wsum, args.ln_eps = wsum.data_ptr(), eps
+    if row_stats is not None:
+        args.flags |= EPI_ROW_STATS
+        args.row_stats, args.row_stats_ld = row_stats.data_ptr(), row_stats.shape[1]
+    _call("gemm", 2.0 * M * N * K, _lib.load().rajni_gemm_bf16_ex, args, _stream(a))
     return out
 
 
@@ -163,8 +180,10 @@ def attention(qkv: torch.Tensor, row_map: Optional[torch.Tensor], B: int, N_src:
 
 
 def patch_im2col(images: torch.Tensor, patch: int, cols: torch.Tensor, cls_pos0: torch.Tensor,
-                 x: torch.Tensor, C: int) -> None:
-    """images [B,3,S,S] fp32|bf16 -> cols [B*P, 3*p*p] bf16; also writes the CLS rows of x."""
+                 x: torch.Tensor, C: int, row_stats: Optional[torch.Tensor] = None, stats_slots: int = 0,
+                 cls_sum: float = 0.0, cls_sumsq: float = 0.0) -> None:
+    """images [B,3,S,S] fp32|bf16 -> cols [B*P, 3*p*p] bf16; also writes the CLS rows of x (and their
+    LayerNorm partial sums into row_stats fp32 [slots, rows, 2])."""
     if images.dtype not in (torch.float32, torch.bfloat16) or not images.is_contiguous():
         raise ValueError("images must be contiguous fp32 or bf16")
     B, ch, S, S2 = images.shape
@@ -172,4 +191,5 @@ def patch_im2col(images: torch.Tensor, patch: int, cols: torch.Tensor, cls_pos0:
         raise ValueError(f"images must be [B,3,S,S], got {tuple(images.shape)}")
     _call("patch_im2col", images.numel() * images.element_size() + images.numel() * 2 + B * C * 2,
           _lib.load().rajni_patch_im2col, images.data_ptr(), int(images.dtype == torch.float32), B, S, patch,
-          cols.data_ptr(), cls_pos0.data_ptr(), x.data_ptr(), C, _stream(images))
+          cols.data_ptr(), cls_pos0.data_ptr(), x.data_ptr(), C, _ptr(row_stats),
+          0 if row_stats is None else row_stats.shape[1], stats_slots, cls_sum, cls_sumsq, _stream(images))

@@ -40,6 +40,25 @@ class PackCache:
         self._store[id(m)] = (sig, packed)
         return packed
 
+    def linear_ln(self, lin: nn.Module, norm: nn.LayerNorm):
+        """LayerNorm folded into the Linear that follows it (model.py:51 -> attention.py:22, model.py:59 -> fc1):
+        (W' = bf16(W*gamma) [N,K], b' = b + W beta fp32 [N], wsum[n] = sum_k W'[n,k] fp32, eps)."""
+        sig = _sig(lin.weight, getattr(lin, "bias", None), norm.weight, norm.bias)
+        key = (id(lin), "ln")
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        w = lin.weight.detach().to(torch.float32)
+        gamma = norm.weight.detach().to(torch.float32)
+        beta = norm.bias.detach().to(torch.float32)
+        wg = (w * gamma[None, :]).to(torch.bfloat16).contiguous()
+        bias = w @ beta
+        if getattr(lin, "bias", None) is not None:
+            bias = bias + lin.bias.detach().to(torch.float32)
+        packed = (wg, bias.contiguous(), wg.to(torch.float32).sum(dim=1).contiguous(), float(norm.eps))
+        self._store[key] = (sig, packed)
+        return packed
+
     def norm(self, m: nn.LayerNorm) -> Tuple[torch.Tensor, torch.Tensor, float]:
         sig = _sig(m.weight, m.bias)
         hit = self._store.get(id(m))

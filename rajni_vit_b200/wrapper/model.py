@@ -128,11 +128,15 @@ class RAJNIViTWrapper(nn.Module):
             P=P, N0=N0, C=C,
             cols=torch.empty((B * P, 768), **bf),
             xa=torch.empty((B * N0, C), **bf), xb=torch.empty((B * N0, C), **bf),
-            xn=torch.empty((B * N0, C), **bf), qkv=torch.empty((B * N0, 3 * C), **bf),
+            qkv=torch.empty((B * N0, 3 * C), **bf),
             att=torch.empty((B * N0, C), **bf), hid=torch.empty((B * N0, hidden), **bf),
             cls=torch.empty((B, C), **bf),
             embed_out_map=((idx // P) * N0 + 1 + idx % P).to(torch.int32),
             embed_pos_map=(1 + idx % P).to(torch.int32),
+            # LayerNorm partial sums (sum, sum of squares) of the rows of x, one slot per (n-tile, column half)
+            # of the GEMM that produced them; consumed by the LN-folded qkv / fc1 GEMMs
+            stat_slots=ops.row_stats_slots(C),
+            stats=torch.zeros((ops.row_stats_slots(C), B * N0, 2), device=dev, dtype=torch.float32),
             sel={},
         )
         self._ws = {key: ws}        # keep one shape resident
@@ -163,14 +167,19 @@ class RAJNIViTWrapper(nn.Module):
         # ---- patch + CLS + pos (model.py:31-37): im2col, then one GEMM whose epilogue adds
         #      bias and pos_embed and scatters into rows 1..P of each image
         pe_w, pe_b = pk.linear(m.patch_embed.proj)
-        pos, cls_pos0 = pk.tensors(
-            ("pos", P), (m.pos_embed, m.cls_token),
-            lambda: (m.pos_embed.detach()[0, : P + 1].to(torch.bfloat16).contiguous(),
-                     (m.cls_token.detach()[0, 0] + m.pos_embed.detach()[0, 0]).to(torch.bfloat16).contiguous()))
+        def _pos_pack():
+            pos_ = m.pos_embed.detach()[0, : P + 1].to(torch.bfloat16).contiguous()
+            cls_ = (m.cls_token.detach()[0, 0] + m.pos_embed.detach()[0, 0]).to(torch.bfloat16).contiguous()
+            c32 = cls_.to(torch.float32)
+            return pos_, cls_, float(c32.sum()), float((c32 * c32).sum())
+
+        pos, cls_pos0, cls_sum, cls_sumsq = pk.tensors(("pos", P), (m.pos_embed, m.cls_token), _pos_pack)
         cur, nxt = ws["xa"], ws["xb"]
-        ops.patch_im2col(x, 16, ws["cols"], cls_pos0, cur, C)
+        stats, slots = ws["stats"], ws["stat_slots"]
+        ops.patch_im2col(x, 16, ws["cols"], cls_pos0, cur, C, row_stats=stats, stats_slots=slots,
+                         cls_sum=cls_sum, cls_sumsq=cls_sumsq)
         ops.gemm(ws["cols"], pe_w, pe_b, B * P, C, 768, residual=pos, ldres=C, res_row_map=ws["embed_pos_map"],
-                 out=cur, ldd=C, out_row_map=ws["embed_out_map"])
+                 out=cur, ldd=C, out_row_map=ws["embed_out_map"], row_stats=stats)
 
         scores = None
         token_counts = []
@@ -178,16 +187,15 @@ class RAJNIViTWrapper(nn.Module):
         for i, blk in enumerate(self.blocks):
             token_counts.append(N)                                                   # model.py:43
             H = blk.attn.num_heads
-            g1, b1, e1 = pk.norm(blk.norm1)
-            g2, b2, e2 = pk.norm(blk.norm2)
-            qw, qb = pk.linear(blk.attn.qkv)
+            # norm1 / norm2 are folded into the qkv / fc1 GEMMs: x itself is the A operand, the row statistics
+            # come from the epilogue of whichever GEMM stored x (embed, proj or fc2)
+            qw, qb, qsum, e1 = pk.linear_ln(blk.attn.qkv, blk.norm1)
             pw, pb = pk.linear(blk.attn.proj)
-            f1w, f1b = pk.linear(blk.mlp.fc1)
+            f1w, f1b, f1sum, e2 = pk.linear_ln(blk.mlp.fc1, blk.norm2)
             f2w, f2b = pk.linear(blk.mlp.fc2)
             hidden = f1w.shape[0]
             M = B * N
-            ops.layernorm(cur, g1, b1, e1, M, C, out=ws["xn"])                        # model.py:51
-            ops.gemm(ws["xn"], qw, qb, M, 3 * C, C, out=ws["qkv"])                    # attention.py:22
+            ops.gemm(cur, qw, qb, M, 3 * C, C, out=ws["qkv"], ln=(stats, slots, qsum, e1))   # model.py:51 + attention.py:22
             if blk.has_pruner:
                 attn: RAJNIAttention = blk.attn
                 keep = keep_count(N, attn.keep_ratio)                                 # attention.py:31-32
@@ -208,7 +216,8 @@ class RAJNIViTWrapper(nn.Module):
                     ops.select(scores, keep, keep_idx=keep_idx, next_scores=next_scores, row_map=row_map)
                 ops.attention(ws["qkv"], row_map, B, N, Np, C, H, float(attn.scale), out=ws["att"])
                 # proj + gathered residual: x_new[b,j] = x[b, keep_idx[b,j]] + proj(att)   model.py:55-58
-                ops.gemm(ws["att"], pw, pb, B * Np, C, C, residual=cur, ldres=C, res_row_map=row_map, out=nxt, ldd=C)
+                ops.gemm(ws["att"], pw, pb, B * Np, C, C, residual=cur, ldres=C, res_row_map=row_map, out=nxt, ldd=C,
+                         row_stats=stats)
                 cur, nxt = nxt, cur
                 scores = next_scores                                                  # attention.py:58
                 keep_log.append(keep_idx)
@@ -216,12 +225,12 @@ class RAJNIViTWrapper(nn.Module):
                 M = B * N
             else:
                 ops.attention(ws["qkv"], None, B, N, N, C, H, float(blk.attn.scale), out=ws["att"])
-                ops.gemm(ws["att"], pw, pb, M, C, C, residual=cur, ldres=C, out=cur, ldd=C)   # in place
+                ops.gemm(ws["att"], pw, pb, M, C, C, residual=cur, ldres=C, out=cur, ldd=C, row_stats=stats)   # in place
                 scores = None                                                         # model.py:63
                 keep_log.append(None)
-            ops.layernorm(cur, g2, b2, e2, M, C, out=ws["xn"])                        # model.py:59
-            ops.gemm(ws["xn"], f1w, f1b, M, hidden, C, gelu=True, out=ws["hid"], ldd=hidden)
-            ops.gemm(ws["hid"], f2w, f2b, M, C, hidden, residual=cur, ldres=C, out=cur, ldd=C)
+            ops.gemm(cur, f1w, f1b, M, hidden, C, gelu=True, out=ws["hid"], ldd=hidden,
+                     ln=(stats, slots, f1sum, e2))                                    # model.py:59 (norm2 + fc1 + GELU)
+            ops.gemm(ws["hid"], f2w, f2b, M, C, hidden, residual=cur, ldres=C, out=cur, ldd=C, row_stats=stats)
 
         # ---- final norm on the CLS rows only (LayerNorm is row-wise) + head   model.py:65-66
         gn, bn, en = pk.norm(m.norm)

@@ -214,6 +214,45 @@ def test_gemm(ops, M, N, K, gelu, res, maps, f32):
     assert not bad.any(), f"{int(bad.sum())} of {bad.numel()} elements out of tolerance; first at {bad.nonzero()[0].tolist()}"
 
 
+@pytest.mark.parametrize("M,C,N,gelu", [(300, 768, 2304, False), (788, 768, 3072, True), (100, 192, 576, False),
+                                        (333, 384, 1536, True), (260, 1024, 3072, False), (40000, 768, 768, False)])
+def test_gemm_layernorm_folded(ops, M, C, N, gelu):
+    """model.py:51/59 folded into the GEMM: a producer GEMM stores x (+ per-row partial sums), the consumer runs on x
+    with gamma-scaled weights.  Reference: torch LayerNorm (fp32) -> Linear (-> GELU) on the same bf16 x."""
+    g = torch.Generator().manual_seed(M + C + N)
+    # producer: x = a @ w0^T + b0 + residual  (bias+residual epilogue with ROW_STATS)
+    a = bf16_round(torch.randn(M, 64, generator=g))
+    w0 = bf16_round(torch.randn(C, 64, generator=g) / 8)
+    b0 = torch.randn(C, generator=g) * 0.5 + 0.3
+    r0 = bf16_round(torch.randn(M, C, generator=g) * 2)
+    slots = ops.row_stats_slots(C)
+    stats = torch.full((slots, M + 7, 2), float("nan"), device="cuda")
+    x = ops.gemm(dev(a, torch.bfloat16), dev(w0, torch.bfloat16), dev(b0), M, C, 64,
+                 residual=dev(r0, torch.bfloat16), ldres=C, row_stats=stats)
+    torch.cuda.synchronize()
+    xf = x.float()
+    tot = stats[:, :M].sum(dim=0).double()
+    torch.testing.assert_close(tot[:, 0], xf.double().sum(dim=1), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(tot[:, 1], (xf.double() ** 2).sum(dim=1), rtol=1e-5, atol=1e-3)
+    assert torch.isnan(stats[:, M:]).all()          # rows past M are never written
+    # consumer
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g) * 0.2
+    w = bf16_round(torch.randn(N, C, generator=g) / math.sqrt(C))
+    bias = torch.randn(N, generator=g)
+    wg = bf16_round(w * gamma[None, :])
+    ref = torch.nn.functional.layer_norm(xf, (C,), dev(gamma), dev(beta), 1e-6) @ dev(wg / gamma[None, :]).t() + dev(bias)
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    out = ops.gemm(x, dev(wg, torch.bfloat16), dev(bias + (wg / gamma[None, :]) @ beta), M, N, C, gelu=gelu,
+                   ln=(stats, slots, dev(wg.sum(dim=1)), 1e-6))
+    torch.cuda.synchronize()
+    report(f"ln-gemm {M}x{N}x{C}", out.float(), ref)
+    tol = BF16_RTOL * ref.abs() + 4e-3
+    bad = (out.float() - ref).abs() > tol
+    assert not bad.any(), f"{int(bad.sum())} of {bad.numel()} elements out of tolerance; first at {bad.nonzero()[0].tolist()}"
+
+
 def test_gelu_matches_erf(ops):
     """The epilogue's GELU is a polynomial form of x*Phi(x); check it against erf over the whole useful range.
     acc = 0 (zero weights), so out[m, n] = gelu(bias[n]) exactly as the epilogue sees fp32 inputs."""
