@@ -266,12 +266,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (valid) orow = p.out_row_map ? (long long)__ldg(p.out_row_map + m) : (long long)m;
                 __nv_bfloat16* const dptr = Dp + orow * p.ldd + ncol0;
                 const __nv_bfloat16* rptr = nullptr;
-                uint32_t rr[2][16];
+                // the whole residual slab of this thread's row (HALF bf16) is requested before the wait for the
+                // accumulator, so its DRAM latency hides behind the MMAs of this tile
+                uint32_t rr[kRes ? NCH : 1][16];
                 if (kRes) {
-                    if (valid) rptr = p.residual + (p.res_row_map ? (long long)__ldg(p.res_row_map + m) : (long long)m) * p.ldres + ncol0;
                     if (valid) {
-                        ldg256_nc(rptr, *reinterpret_cast<uint32_t(*)[8]>(&rr[0][0]));
-                        ldg256_nc(rptr + 16, *reinterpret_cast<uint32_t(*)[8]>(&rr[0][8]));
+                        rptr = p.residual + (p.res_row_map ? (long long)__ldg(p.res_row_map + m) : (long long)m) * p.ldres + ncol0;
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) {
+                            ldg256_nc(rptr + c * 32, *reinterpret_cast<uint32_t(*)[8]>(&rr[c][0]));
+                            ldg256_nc(rptr + c * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rr[c][8]));
+                        }
                     }
                 }
                 uint64_t rstd2 = 0, mr2 = 0;
@@ -312,10 +317,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             else mbar_arrive(&tmem_empty[acc]);
                         }
                     }
-                    if (kRes && ch + 1 < NCH && valid) {
-                        ldg256_nc(rptr + (ch + 1) * 32, *reinterpret_cast<uint32_t(*)[8]>(&rr[(ch + 1) & 1][0]));
-                        ldg256_nc(rptr + (ch + 1) * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rr[(ch + 1) & 1][8]));
-                    }
                     uint32_t o[16];
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -335,7 +336,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             x23 = gelu_erf2(x23);
                         }
                         if (kRes) {
-                            const float2 r0 = bf16x2_to_float2(rr[ch & 1][j >> 1]), r1 = bf16x2_to_float2(rr[ch & 1][(j >> 1) + 1]);
+                            const float2 r0 = bf16x2_to_float2(rr[kRes ? ch : 0][j >> 1]), r1 = bf16x2_to_float2(rr[kRes ? ch : 0][(j >> 1) + 1]);
                             x01 = add2(x01, f2pack(r0.x, r0.y));
                             x23 = add2(x23, f2pack(r1.x, r1.y));
                         }

@@ -145,7 +145,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], M: int,
          gelu: bool = False, residual: Optional[torch.Tensor] = None, ldres: Optional[int] = None,
          res_row_map: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
          ldd: Optional[int] = None, out_row_map: Optional[torch.Tensor] = None, out_f32: bool = False,
-         ln: Optional[tuple] = None, row_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+         ln: Optional[tuple] = None, row_stats: Optional[torch.Tensor] = None, tag: str = "") -> torch.Tensor:
     """out[orow(m), n] = epi(sum_k a[m,k] w[n,k]); a [M,K] bf16, w [N,K] bf16, bias fp32 [N].
 
     ``ln = (stats, slots, wsum, eps)``: LayerNorm folded in (a is the un-normalised x, w = W*gamma,
@@ -166,7 +166,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], M: int,
     if row_stats is not None:
         args.flags |= EPI_ROW_STATS
         args.row_stats, args.row_stats_ld = row_stats.data_ptr(), row_stats.shape[1]
-    _call("gemm", 2.0 * M * N * K, _lib.load().rajni_gemm_bf16_ex, args, _stream(a))
+    _call("gemm:" + tag if tag else "gemm", 2.0 * M * N * K, _lib.load().rajni_gemm_bf16_ex, args, _stream(a))
     return out
 
 

@@ -179,7 +179,7 @@ class RAJNIViTWrapper(nn.Module):
         ops.patch_im2col(x, 16, ws["cols"], cls_pos0, cur, C, row_stats=stats, stats_slots=slots,
                          cls_sum=cls_sum, cls_sumsq=cls_sumsq)
         ops.gemm(ws["cols"], pe_w, pe_b, B * P, C, 768, residual=pos, ldres=C, res_row_map=ws["embed_pos_map"],
-                 out=cur, ldd=C, out_row_map=ws["embed_out_map"], row_stats=stats)
+                 out=cur, ldd=C, out_row_map=ws["embed_out_map"], row_stats=stats, tag="embed")
 
         scores = None
         token_counts = []
@@ -195,7 +195,7 @@ class RAJNIViTWrapper(nn.Module):
             f2w, f2b = pk.linear(blk.mlp.fc2)
             hidden = f1w.shape[0]
             M = B * N
-            ops.gemm(cur, qw, qb, M, 3 * C, C, out=ws["qkv"], ln=(stats, slots, qsum, e1))   # model.py:51 + attention.py:22
+            ops.gemm(cur, qw, qb, M, 3 * C, C, out=ws["qkv"], ln=(stats, slots, qsum, e1), tag="qkv")   # model.py:51 + attention.py:22
             if blk.has_pruner:
                 attn: RAJNIAttention = blk.attn
                 keep = keep_count(N, attn.keep_ratio)                                 # attention.py:31-32
@@ -217,7 +217,7 @@ class RAJNIViTWrapper(nn.Module):
                 ops.attention(ws["qkv"], row_map, B, N, Np, C, H, float(attn.scale), out=ws["att"])
                 # proj + gathered residual: x_new[b,j] = x[b, keep_idx[b,j]] + proj(att)   model.py:55-58
                 ops.gemm(ws["att"], pw, pb, B * Np, C, C, residual=cur, ldres=C, res_row_map=row_map, out=nxt, ldd=C,
-                         row_stats=stats)
+                         row_stats=stats, tag="proj")
                 cur, nxt = nxt, cur
                 scores = next_scores                                                  # attention.py:58
                 keep_log.append(keep_idx)
@@ -225,18 +225,18 @@ class RAJNIViTWrapper(nn.Module):
                 M = B * N
             else:
                 ops.attention(ws["qkv"], None, B, N, N, C, H, float(blk.attn.scale), out=ws["att"])
-                ops.gemm(ws["att"], pw, pb, M, C, C, residual=cur, ldres=C, out=cur, ldd=C, row_stats=stats)   # in place
+                ops.gemm(ws["att"], pw, pb, M, C, C, residual=cur, ldres=C, out=cur, ldd=C, row_stats=stats, tag="proj")   # in place
                 scores = None                                                         # model.py:63
                 keep_log.append(None)
             ops.gemm(cur, f1w, f1b, M, hidden, C, gelu=True, out=ws["hid"], ldd=hidden,
-                     ln=(stats, slots, f1sum, e2))                                    # model.py:59 (norm2 + fc1 + GELU)
-            ops.gemm(ws["hid"], f2w, f2b, M, C, hidden, residual=cur, ldres=C, out=cur, ldd=C, row_stats=stats)
+                     ln=(stats, slots, f1sum, e2), tag="fc1")                                    # model.py:59 (norm2 + fc1 + GELU)
+            ops.gemm(ws["hid"], f2w, f2b, M, C, hidden, residual=cur, ldres=C, out=cur, ldd=C, row_stats=stats, tag="fc2")
 
         # ---- final norm on the CLS rows only (LayerNorm is row-wise) + head   model.py:65-66
         gn, bn, en = pk.norm(m.norm)
         hw, hb = pk.linear(m.head)
         ops.layernorm(cur, gn, bn, en, B, C, in_row_stride=N * C, out=ws["cls"])
-        logits = ops.gemm(ws["cls"], hw, hb, B, hw.shape[0], C, out_f32=True)
+        logits = ops.gemm(ws["cls"], hw, hb, B, hw.shape[0], C, out_f32=True, tag="head")
 
         self._last_stats = {"token_counts": token_counts}                            # model.py:68
         self._last_keep_idx = keep_log

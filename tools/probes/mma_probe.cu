@@ -81,7 +81,46 @@ __global__ void __launch_bounds__(256) ldtm_kernel(int reps, int st, long long* 
     if (warp == 0) { tc_fence_after(); tmem_dealloc(slot, 512); }
 }
 
+// MUFU.EX2 / FFMA / FFMA2 issue rates: `warps` warps, 8 independent chains per thread
+__global__ void __launch_bounds__(1024) alu_kernel(int which, int reps, long long* out, float* sink) {
+    float x[8];
+    uint64_t y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[i] = threadIdx.x * 1e-3f + i; y[i] = f2pack(x[i], x[i] + 0.5f); }
+    const uint64_t c2 = f2pack(0.999f, 1.001f), d2 = f2pack(1e-3f, 2e-3f);
+    __syncthreads();
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (which == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+            else if (which == 1) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(0.999f), "f"(1e-3f));
+            else asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(y[i]) : "l"(c2), "l"(d2));
+        }
+    }
+    long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) out[0] = t1 - t0;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { float a, b; f2unpack(y[i], a, b); acc += x[i] + a + b; }
+    sink[threadIdx.x] = acc;
+}
+
 int main() {
+    {
+        long long* o; float* sk;
+        cudaMallocManaged(&o, 64); cudaMallocManaged(&sk, 4096 * 4);
+        const char* nm[] = {"MUFU.EX2", "FFMA", "FFMA2"};
+        for (int which = 0; which < 3; ++which)
+            for (int warps : {4, 8, 16, 32}) {
+                alu_kernel<<<1, warps * 32>>>(which, 256, o, sk);
+                cudaDeviceSynchronize();
+                alu_kernel<<<1, warps * 32>>>(which, 256, o, sk);
+                cudaDeviceSynchronize();
+                printf("%-8s %2d warps: %.2f lane-ops/clk/SM\n", nm[which], warps, 256.0 * 8 * warps * 32 / (double)o[0]);
+            }
+    }
     long long* out; uint32_t* sink;
     cudaMallocManaged(&out, 4096); cudaMallocManaged(&sink, 1 << 20);
     cudaFuncSetAttribute(mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
