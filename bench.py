@@ -39,6 +39,7 @@ SCHEDULE = {3: {"keep_ratio": 0.88, "update": True}, 4: {"keep_ratio": 0.88, "up
             7: {"keep_ratio": 0.8, "update": True}, 8: {"keep_ratio": 0.72, "update": True}}
 BATCH = 256
 METRIC = "ViT-B/16 RAJNI images/sec @bs256"
+WORKLOAD = f"C2: {MODEL} random-init + README schedule {{3:.88,4:.88,7:.8,8:.72}}, 224px, bf16 batch 256 per GPU"
 TOKENS = [197, 197, 197, 197, 173, 152, 152, 152, 121, 87, 87, 87]
 
 
@@ -103,12 +104,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_port(batch, steps, warmup, threads=None):
+def host_threads() -> int:
+    """Every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which is not what the CPU leg wants)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def cpu_port(batch, steps, warmup):
     """Time the CPU oracle port of the reference path (fp32, all host threads)."""
     from oracle import rajni_oracle as orc
     from rajni_vit_b200.vit import create_model
-    if threads:
-        torch.set_num_threads(threads)
     params = orc.extract_params(create_model(MODEL, seed=0))
     g = torch.Generator().manual_seed(1234)
     images = torch.randn(batch, 3, 224, 224, generator=g)
@@ -125,7 +134,7 @@ def run_reference(args):
     """--impl reference: the reference path's CPU implementation (oracle port), rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    cores = torch.get_num_threads()
+    cores = host_threads()
     ips4, t4 = cpu_port(4, 1, 1)
     budget = 150.0 / max(1, args.steps + args.warmup)           # seconds per step
     batch = int(max(1, min(32, budget / (t4 / 4))))
@@ -135,7 +144,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(ips, 2), "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t_step * 1e3, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C2: {MODEL} README schedule {{3:.88,4:.88,7:.8,8:.72}}", "sample_batch": batch},
+        "config": {"workload": WORKLOAD, "sample_batch": batch},
         "cpu_baseline": {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(ips, 2), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -152,10 +161,11 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU batch (default = BASELINE config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
 
     if args.impl == "reference":
+        args.warmup = max(args.warmup, 1)
         return run_reference(args)
+    args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
     from rajni_vit_b200 import RAJNIViTWrapper, _lib, ops
@@ -269,7 +279,7 @@ def main():
             "metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"C2: {MODEL} random-init + README schedule {{3:.88,4:.88,7:.8,8:.72}}, 224px",
+            "config": {"workload": WORKLOAD,
                        "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "two alternating 154 MB input batches and >1 GB of activations per step (larger than the 126 MB L2)",
                        "token_counts": TOKENS, "gflop_per_image": round(flops_img / 1e9, 3)},
@@ -280,7 +290,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cores = torch.get_num_threads()
+            cores = host_threads()
             ips, t_step = cpu_port(16, 2, 1)
             out["cpu_baseline"] = {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": "port",
                                    "sample": f"3 forwards (1 warm-up + 2 timed) of 16 images, oracle port of the reference path, fp32, {cores} threads"}
