@@ -81,6 +81,38 @@ __global__ void __launch_bounds__(256) ldtm_kernel(int reps, int st, long long* 
     if (warp == 0) { tc_fence_after(); tmem_dealloc(slot, 512); }
 }
 
+// LDTM shapes: 0 = 32x32b.x32 (4 KB), 1 = 16x256b.x8 (4 KB), 2 = 16x256b.x4 (2 KB); `depth` loads in flight per wait
+__global__ void __launch_bounds__(512) ldtm2_kernel(int shape, int depth, int reps, long long* out, uint32_t* sink) {
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) tmem_alloc(&slot, 512);
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t trow = slot + ((uint32_t)((warp & 3) * 32 + ((warp >> 2) & 1) * 16 * (shape != 0)) << 16) + (warp >> 3) * 256;
+    uint32_t acc = 0;
+    __syncthreads();
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+        uint32_t a[32], b[32], c[16], d[16];
+        if (shape == 0) { tmem_ld32(trow, a); if (depth > 1) tmem_ld32(trow + 32, b); }
+        else if (shape == 1) { tmem_ld16x256_x8(trow, a); if (depth > 1) tmem_ld16x256_x8(trow + 64, b); }
+        else { tmem_ld16x256_x4(trow, c); if (depth > 1) tmem_ld16x256_x4(trow + 32, d); }
+        tmem_ld_wait();
+        if (shape < 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc ^= a[j] ^ (depth > 1 ? b[j] : 0u);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc ^= c[j] ^ (depth > 1 ? d[j] : 0u);
+        }
+    }
+    long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) out[0] = t1 - t0;
+    sink[threadIdx.x] = acc;
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(slot, 512); }
+}
+
 // MUFU.EX2 / FFMA / FFMA2 issue rates: `warps` warps, 8 independent chains per thread
 __global__ void __launch_bounds__(1024) alu_kernel(int which, int reps, long long* out, float* sink) {
     float x[8];
@@ -146,6 +178,21 @@ int main() {
             printf("%s M=128 N= 64 K=16, %d independent accumulators: issue %.1f cyc/mma, complete %.1f cyc/mma\n", names[mode], nacc,
                    (double)out[0] / reps, (double)out[1] / reps);
         }
+    {
+        const char* shp[] = {"32x32b.x32 (4KB)", "16x256b.x8 (4KB)", "16x256b.x4 (2KB)"};
+        const int bytes[] = {4096, 4096, 2048};
+        for (int shape = 0; shape < 3; ++shape)
+            for (int depth : {1, 2})
+                for (int warps : {4, 8, 16}) {
+                    ldtm2_kernel<<<1, warps * 32>>>(shape, depth, 512, out, sink);
+                    cudaDeviceSynchronize();
+                    ldtm2_kernel<<<1, warps * 32>>>(shape, depth, 512, out, sink);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    if (e != cudaSuccess) { printf("ldtm2: %s\n", cudaGetErrorString(e)); return 1; }
+                    printf("LDTM %s depth %d, %2d warps: %.1f cyc per wait, %.1f B/cyc/SM\n", shp[shape], depth, warps,
+                           (double)out[0] / 512, (double)bytes[shape] * depth * warps * 512 / out[0]);
+                }
+    }
     for (int st = 0; st < 2; ++st)
         for (int warps : {1, 4, 8}) {
             ldtm_kernel<<<1, warps * 32>>>(512, st, out, sink);
