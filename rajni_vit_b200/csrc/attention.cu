@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const AttnParams
     const int g = lane >> 2, tig = lane & 3;
     const int q0 = qt * kAttBQ;
     const int nkb = (p.Np + kAttBK - 1) / kAttBK;
+    griddep_launch();
+    griddep_wait();
 
     load_tile(s_q, p, b, h, 0, q0);
     load_tile(s_k[0], p, b, h, 1, 0);
@@ -219,7 +221,8 @@ extern "C" int rajni_attention_fwd(const void* qkv, const int32_t* row_map, void
     p.N_src = N_src; p.Np = Np; p.C = C; p.H = H;
     p.scale_log2 = scale * 1.4426950408889634f;
     dim3 grid((Np + kAttBQ - 1) / kAttBQ, H, B);
-    attention_kernel<<<grid, kAttThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    cudaError_t le = launch_kernel(attention_kernel, grid, dim3(kAttThreads), 0, static_cast<cudaStream_t>(stream), 1, p);
+    RAJNI_REQUIRE(le == cudaSuccess, RAJNI_ECUDA, "attention_fwd: launch failed: %s", cudaGetErrorString(le));
     count_launch();
     return check_launch("attention_fwd");
 }

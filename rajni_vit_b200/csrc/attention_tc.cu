@@ -125,6 +125,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPa
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch();
+    griddep_wait();
     const int n_mine = (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // units of this CTA
 
     if (warp >= kAtLoaderWarp0 && p.row_map == nullptr) {
@@ -484,8 +486,9 @@ int launch_attention_tc(const void* qkv, const int32_t* row_map, void* out, int 
         attr_smem = smem;
     }
     const int grid = p.n_units < at_num_sms() ? p.n_units : at_num_sms();
-    attention_tc_kernel<<<grid, kAtThreads, smem, stream>>>(tmap, p);
+    cudaError_t le = launch_kernel(attention_tc_kernel, dim3(grid), dim3(kAtThreads), (size_t)smem, stream, 1, tmap, p);
     count_launch();
+    RAJNI_REQUIRE(le == cudaSuccess, RAJNI_ECUDA, "attention_tc: launch failed: %s", cudaGetErrorString(le));
     int rc = check_launch("attention_tc");
     return rc ? rc : 1;
 }

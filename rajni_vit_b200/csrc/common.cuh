@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "../../include/rajni_b200.h"
 
 namespace rajni {
@@ -22,6 +24,43 @@ int check_launch(const char* what);   // cudaGetLastError -> RAJNI_ECUDA
             return (code);                        \
         }                                         \
     } while (0)
+
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of the path is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may start
+// (set up shared memory, barriers, TMEM, descriptors) while its predecessor in the stream is still draining, and
+// blocks in griddep_wait() until that predecessor has completed and flushed before it touches global memory.
+// griddep_launch() lets the NEXT kernel do the same with respect to this one.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();      // capi.cu: false when RAJNI_NO_PDL is set
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 int cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // ------------------------------------------------------------------ small device utils
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

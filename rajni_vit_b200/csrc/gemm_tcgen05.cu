@@ -169,6 +169,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch();
+    griddep_wait();          // everything above overlapped the previous kernel's tail; global memory from here on
 
     if (warp == kTmaWarp) {
         // ================= TMA producer (one lane per CTA) =================
@@ -551,19 +553,8 @@ static int launch_gemm_mode(const void* A, const void* W, GemmParams& p, cudaStr
     int grid = p.tiles_m * p.tiles_n * CG;
     const int max_grid = (num_sms() / CG) * CG;
     if (grid > max_grid) grid = max_grid;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG, MODE, LN>, ta, tb, p);
+    cudaError_t e = launch_kernel(gemm_bf16_kernel<BN, CG, MODE, LN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, CG,
+                                  ta, tb, p);
     count_launch();
     RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "gemm_bf16: launch failed: %s", cudaGetErrorString(e));
     return check_launch("gemm_bf16");

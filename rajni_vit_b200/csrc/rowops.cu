@@ -10,6 +10,8 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint4* __restric
                                                           const int32_t* __restrict__ row_map,
                                                           uint4* __restrict__ dst,
                                                           long long total_chunks, int chunks_per_row) {
+    griddep_launch();
+    griddep_wait();
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     // 4 independent 16-byte loads in flight per thread
@@ -40,6 +42,8 @@ template <int CPL>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long in_stride,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, __nv_bfloat16* __restrict__ y, int rows, int C) {
+    griddep_launch();
+    griddep_wait();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -102,6 +106,8 @@ __global__ void __launch_bounds__(256) im2col16_kernel(const void* __restrict__ 
                                                        uint4* __restrict__ x, int C,
                                                        float2* __restrict__ row_stats, long long stats_ld, int stats_slots,
                                                        float cls_sum, float cls_sumsq) {
+    griddep_launch();
+    griddep_wait();
     const int G = S >> 4;                       // patches per side
     const long long strips = (long long)B * G * 3 * 16 * G;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -160,9 +166,10 @@ extern "C" int rajni_gather_rows(const void* src, const int32_t* row_map, void* 
     const long long total = (long long)rows_out * cpr;
     long long blocks = (total + 256 * 4 - 1) / (256 * 4);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    gather_rows_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint4*>(src), row_map, static_cast<uint4*>(dst), total, cpr);
+    cudaError_t e = launch_kernel(gather_rows_kernel, dim3((int)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+                                  static_cast<const uint4*>(src), row_map, static_cast<uint4*>(dst), total, cpr);
     count_launch();
+    RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "gather_rows: launch failed: %s", cudaGetErrorString(e));
     return check_launch("gather_rows");
 }
 
@@ -177,14 +184,16 @@ extern "C" int rajni_layernorm(const void* x, long long in_row_stride, const flo
     auto s = static_cast<cudaStream_t>(stream);
     auto xb = static_cast<const __nv_bfloat16*>(x);
     auto yb = static_cast<__nv_bfloat16*>(y);
+    cudaError_t le = cudaSuccess;
     switch (cpl) {
-        case 1: layernorm_kernel<1><<<grid, block, 0, s>>>(xb, in_row_stride, gamma, beta, eps, yb, rows, C); break;
-        case 2: layernorm_kernel<2><<<grid, block, 0, s>>>(xb, in_row_stride, gamma, beta, eps, yb, rows, C); break;
-        case 3: layernorm_kernel<3><<<grid, block, 0, s>>>(xb, in_row_stride, gamma, beta, eps, yb, rows, C); break;
-        case 4: layernorm_kernel<4><<<grid, block, 0, s>>>(xb, in_row_stride, gamma, beta, eps, yb, rows, C); break;
-        default: layernorm_kernel<8><<<grid, block, 0, s>>>(xb, in_row_stride, gamma, beta, eps, yb, rows, C); break;
+        case 1: le = launch_kernel(layernorm_kernel<1>, grid, block, 0, s, 1, xb, in_row_stride, gamma, beta, eps, yb, rows, C); break;
+        case 2: le = launch_kernel(layernorm_kernel<2>, grid, block, 0, s, 1, xb, in_row_stride, gamma, beta, eps, yb, rows, C); break;
+        case 3: le = launch_kernel(layernorm_kernel<3>, grid, block, 0, s, 1, xb, in_row_stride, gamma, beta, eps, yb, rows, C); break;
+        case 4: le = launch_kernel(layernorm_kernel<4>, grid, block, 0, s, 1, xb, in_row_stride, gamma, beta, eps, yb, rows, C); break;
+        default: le = launch_kernel(layernorm_kernel<8>, grid, block, 0, s, 1, xb, in_row_stride, gamma, beta, eps, yb, rows, C); break;
     }
     count_launch();
+    RAJNI_REQUIRE(le == cudaSuccess, RAJNI_ECUDA, "layernorm: launch failed: %s", cudaGetErrorString(le));
     return check_launch("layernorm");
 }
 
@@ -202,14 +211,11 @@ extern "C" int rajni_patch_im2col(const void* images, int images_f32, int B, int
     long long blocks = (strips + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     auto s = static_cast<cudaStream_t>(stream);
-    if (images_f32)
-        im2col16_kernel<true><<<(int)blocks, 256, 0, s>>>(images, B, S, static_cast<__nv_bfloat16*>(cols),
-                                                          static_cast<const uint4*>(cls_pos0), static_cast<uint4*>(x), C,
-                                                          reinterpret_cast<float2*>(row_stats), row_stats_ld, stats_slots, cls_sum, cls_sumsq);
-    else
-        im2col16_kernel<false><<<(int)blocks, 256, 0, s>>>(images, B, S, static_cast<__nv_bfloat16*>(cols),
-                                                           static_cast<const uint4*>(cls_pos0), static_cast<uint4*>(x), C,
-                                                           reinterpret_cast<float2*>(row_stats), row_stats_ld, stats_slots, cls_sum, cls_sumsq);
+    cudaError_t le = launch_kernel(images_f32 ? im2col16_kernel<true> : im2col16_kernel<false>, dim3((int)blocks), dim3(256), 0, s, 1,
+                                   images, B, S, static_cast<__nv_bfloat16*>(cols), static_cast<const uint4*>(cls_pos0),
+                                   static_cast<uint4*>(x), C, reinterpret_cast<float2*>(row_stats), row_stats_ld, stats_slots,
+                                   cls_sum, cls_sumsq);
     count_launch();
+    RAJNI_REQUIRE(le == cudaSuccess, RAJNI_ECUDA, "patch_im2col: launch failed: %s", cudaGetErrorString(le));
     return check_launch("patch_im2col");
 }

@@ -167,6 +167,8 @@ __global__ void __launch_bounds__(kSelThreads) score_select_kernel(const ScoreSe
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x;
 
+    griddep_launch();
+    griddep_wait();
     float* s_score = smem;                         // [N]
     float* s_scratch = s_score + N;                // [64 * 8] reduction scratch (also 16-warp scratch)
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_scratch + 512);   // [256]
@@ -322,8 +324,9 @@ static int launch_score_select(const ScoreSelectParams& p, int B, cudaStream_t s
     }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "score_select: smem attribute: %s", cudaGetErrorString(e));
-    kern<<<B, kSelThreads, smem, stream>>>(p);
+    e = launch_kernel(kern, dim3(B), dim3(kSelThreads), smem, stream, 1, p);
     count_launch();
+    RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "score_select: launch failed: %s", cudaGetErrorString(e));
     return check_launch("score_select");
 }
 
