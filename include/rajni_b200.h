@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RAJNI_ABI_VERSION 2
+#define RAJNI_ABI_VERSION 3
 
 enum {
     RAJNI_OK = 0,
@@ -44,7 +44,9 @@ enum {
     RAJNI_EPI_RESIDUAL = 4,   /* + residual[res_row(m), n] after activation      */
     RAJNI_EPI_OUT_F32 = 8,    /* store fp32 instead of bf16                      */
     RAJNI_EPI_LN_FOLD = 16,   /* A is the UN-normalised x; apply LayerNorm algebraically (see below)  */
-    RAJNI_EPI_ROW_STATS = 32  /* also emit per-row partial (sum, sum of squares) of the stored values */
+    RAJNI_EPI_ROW_STATS = 32, /* also emit per-row partial (sum, sum of squares) of the stored values */
+    RAJNI_HINT_REVERSE_M = 64 /* walk the M tiles last-to-first: a consumer that starts where its producer
+                                 finished finds those rows still in the 126 MB L2. Results are identical.   */
 };
 
 int rajni_abi_version(void);
@@ -121,9 +123,10 @@ int rajni_gemm_row_stats_slots(int N);
 /* ---- a4: multi-head attention over kept tokens (attention.py:45-54)
  * qkv [B,N_src,3C] bf16; when row_map != NULL token j of image b is read from
  * global row row_map[b*Np+j] (gather fused into the loads), else N_src == Np.
- * out [B,Np,C] bf16 = softmax(q k^T * scale) v, heads concatenated. D must be 64. */
+ * out [B,Np,C] bf16 = softmax(q k^T * scale) v, heads concatenated. D must be 64.
+ * reverse != 0: process the images last-to-first (L2 reuse hint, see RAJNI_HINT_REVERSE_M). */
 int rajni_attention_fwd(const void* qkv, const int32_t* row_map, void* out,
-                        int B, int N_src, int Np, int C, int H, float scale, void* stream);
+                        int B, int N_src, int Np, int C, int H, float scale, int reverse, void* stream);
 
 /* ---- a8: patch-embed front end (model.py:31-37)
  * im2col: images [B,3,S,S] (fp32 if images_f32 else bf16) -> cols [B*P, 3*p*p] bf16

@@ -194,14 +194,14 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const AttnParams
 }
 
 int launch_attention_tc(const void* qkv, const int32_t* row_map, void* out, int B, int N_src, int Np,
-                        int C, int H, float scale, cudaStream_t stream);   // attention_tc.cu
+                        int C, int H, float scale, int reverse, cudaStream_t stream);   // attention_tc.cu
 
 }  // namespace rajni
 
 using namespace rajni;
 
 extern "C" int rajni_attention_fwd(const void* qkv, const int32_t* row_map, void* out,
-                                   int B, int N_src, int Np, int C, int H, float scale, void* stream) {
+                                   int B, int N_src, int Np, int C, int H, float scale, int reverse, void* stream) {
     RAJNI_REQUIRE(qkv && out, RAJNI_EINVAL, "rajni_attention_fwd: null pointer");
     RAJNI_REQUIRE(B > 0 && Np > 0 && N_src >= Np && H > 0 && C == H * 64, RAJNI_EINVAL,
                   "rajni_attention_fwd: B=%d N_src=%d Np=%d C=%d H=%d (head dim must be 64)", B, N_src, Np, C, H);
@@ -211,7 +211,7 @@ extern "C" int rajni_attention_fwd(const void* qkv, const int32_t* row_map, void
     // kernel below covers longer sequences (577-token config) until the multi-block version lands.
     static const bool legacy = getenv("RAJNI_ATTN_LEGACY") != nullptr;
     if (!legacy) {
-        int rc = launch_attention_tc(qkv, row_map, out, B, N_src, Np, C, H, scale, static_cast<cudaStream_t>(stream));
+        int rc = launch_attention_tc(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, static_cast<cudaStream_t>(stream));
         if (rc != 0) return rc < 0 ? rc : RAJNI_OK;
     }
     AttnParams p{};

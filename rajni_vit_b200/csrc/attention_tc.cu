@@ -52,6 +52,7 @@ struct AttnTcParams {
     int N_src, Np, Np_pad, C, H, BH, two_tiles, n_units;
     int o_col, o_outside;       // TMEM column of O inside a tile; o_outside = O does not overlap S's columns
     int plane_bytes, stages;    // bytes of one Q/K/V plane of a stage (1024-aligned); pipeline depth
+    int reverse;                // walk the (image, head) items last-to-first (L2 reuse hint)
     float scale_log2;
 };
 
@@ -79,9 +80,9 @@ __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
 
 // (image*H + head) handled by tile `t` of unit `u`, or -1
 __device__ __forceinline__ int unit_item(const AttnTcParams& p, int u, int t) {
-    if (p.two_tiles) return u;
-    const int item = 2 * u + t;
-    return item < p.BH ? item : -1;
+    const int item = p.two_tiles ? u : 2 * u + t;
+    if (item >= p.BH) return -1;
+    return p.reverse ? p.BH - 1 - item : item;
 }
 
 __global__ void __launch_bounds__(kAtThreads, 1)
@@ -456,13 +457,14 @@ static int at_num_sms() {
 
 // returns 1 if the tcgen05 kernel handled the call, 0 if the shape is outside its range, <0 on error
 int launch_attention_tc(const void* qkv, const int32_t* row_map, void* out, int B, int N_src, int Np,
-                        int C, int H, float scale, cudaStream_t stream) {
+                        int C, int H, float scale, int reverse, cudaStream_t stream) {
     if (Np > 256) return 0;
     AttnTcParams p{};
     p.qkv = static_cast<const __nv_bfloat16*>(qkv);
     p.row_map = row_map;
     p.out = static_cast<__nv_bfloat16*>(out);
     p.N_src = N_src; p.Np = Np; p.C = C; p.H = H;
+    p.reverse = reverse;
     p.BH = B * H;
     p.Np_pad = (Np + 15) & ~15;
     p.two_tiles = Np > 128;

@@ -64,6 +64,7 @@ struct GemmParams {
     long long ldd, ldres;
     int M, N, K, flags;
     int tiles_m, tiles_n, k_blocks;
+    int reverse_m;              // walk the M tiles from the last to the first (L2 reuse hint, results identical)
     // LayerNorm folding
     const float2* ln_stats;     // [ln_slots][ln_stats_ld] partial (sum, sumsq) of the rows of A
     const float* ln_wsum;       // [N] sum_k W'[n,k]
@@ -178,7 +179,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
-                const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+                const int m_lin = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+                const int m_blk = p.reverse_m ? p.tiles_m - 1 - m_lin : m_lin;
                 const int row_a = m_blk * (BM * CG) + (int)cta_rank * BM;
                 const int row_b = n_blk * BN + (int)cta_rank * Cfg::kBRows;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -247,7 +249,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             __nv_bfloat16* const Dp = static_cast<__nv_bfloat16*>(p.D);
             int local = 0;
             for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++local) {
-                const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+                const int m_lin = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+                const int m_blk = p.reverse_m ? p.tiles_m - 1 - m_lin : m_lin;
                 const int acc = local & 1;
                 const uint32_t acc_phase = (local >> 1) & 1;
                 const int m = m_blk * (BM * CG) + (int)cta_rank * BM + sub * 32 + lane;
@@ -387,7 +390,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         int local = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++local) {
-            const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+            const int m_lin = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+            const int m_blk = p.reverse_m ? p.tiles_m - 1 - m_lin : m_lin;
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
             const int row0 = m_blk * (BM * CG) + (int)cta_rank * BM + sub * 32;
@@ -567,7 +571,7 @@ static bool aligned32(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr
 template <int BN, int CG>
 static int launch_gemm(const void* A, const void* W, GemmParams& p, cudaStream_t stream) {
     const int ln = p.flags & RAJNI_EPI_LN_FOLD, stats = p.flags & RAJNI_EPI_ROW_STATS;
-    const int core = p.flags & ~(RAJNI_EPI_LN_FOLD | RAJNI_EPI_ROW_STATS);
+    const int core = p.flags & ~(RAJNI_EPI_LN_FOLD | RAJNI_EPI_ROW_STATS | RAJNI_HINT_REVERSE_M);
     bool hot = p.N % BN == 0 && p.ldd % 16 == 0 && aligned32(p.D);
     if (core & RAJNI_EPI_RESIDUAL) hot = hot && p.ldres % 16 == 0 && aligned32(p.residual);
     if (hot) {
@@ -625,7 +629,8 @@ extern "C" int rajni_gemm_bf16_ex(const rajni_gemm_args* a, void* stream) {
     p.residual = static_cast<const __nv_bfloat16*>(a->residual);
     p.res_row_map = a->res_row_map; p.out_row_map = a->out_row_map;
     p.ldd = a->ldd; p.ldres = a->ldres;
-    p.M = M; p.N = N; p.K = K; p.flags = flags;
+    p.M = M; p.N = N; p.K = K; p.flags = flags & ~RAJNI_HINT_REVERSE_M;
+    p.reverse_m = (flags & RAJNI_HINT_REVERSE_M) != 0;
     p.ln_stats = reinterpret_cast<const float2*>(a->ln_stats);
     p.ln_wsum = a->ln_wsum;
     p.ln_stats_ld = a->ln_stats_ld;

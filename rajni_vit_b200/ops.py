@@ -8,7 +8,8 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import EPI_BIAS, EPI_GELU, EPI_LN_FOLD, EPI_OUT_F32, EPI_RESIDUAL, EPI_ROW_STATS  # noqa: F401  (re-exported)
+from ._lib import (EPI_BIAS, EPI_GELU, EPI_LN_FOLD, EPI_OUT_F32, EPI_RESIDUAL, EPI_ROW_STATS,  # noqa: F401  (re-exported)
+                   HINT_REVERSE_M)
 
 _checked_devices = set()
 _prof = None        # list of (name, work, start_event, end_event) while profile_steps() runs
@@ -145,14 +146,17 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], M: int,
          gelu: bool = False, residual: Optional[torch.Tensor] = None, ldres: Optional[int] = None,
          res_row_map: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
          ldd: Optional[int] = None, out_row_map: Optional[torch.Tensor] = None, out_f32: bool = False,
-         ln: Optional[tuple] = None, row_stats: Optional[torch.Tensor] = None, tag: str = "") -> torch.Tensor:
+         ln: Optional[tuple] = None, row_stats: Optional[torch.Tensor] = None, tag: str = "",
+         reverse: bool = False) -> torch.Tensor:
     """out[orow(m), n] = epi(sum_k a[m,k] w[n,k]); a [M,K] bf16, w [N,K] bf16, bias fp32 [N].
 
     ``ln = (stats, slots, wsum, eps)``: LayerNorm folded in (a is the un-normalised x, w = W*gamma,
     bias = b + W beta, wsum[n] = sum_k w[n,k], stats fp32 [>=slots, rows, 2] partial sums of x's rows).
-    ``row_stats`` fp32 [slots, rows, 2]: also emit the partial sums of the rows this GEMM stores."""
+    ``row_stats`` fp32 [slots, rows, 2]: also emit the partial sums of the rows this GEMM stores.
+    ``reverse``: walk the M tiles last-to-first (L2 reuse hint; results identical)."""
     flags = (EPI_BIAS if bias is not None else 0) | (EPI_GELU if gelu else 0) | \
-            (EPI_RESIDUAL if residual is not None else 0) | (EPI_OUT_F32 if out_f32 else 0)
+            (EPI_RESIDUAL if residual is not None else 0) | (EPI_OUT_F32 if out_f32 else 0) | \
+            (HINT_REVERSE_M if reverse else 0)
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
     args = _lib.GemmArgs(a.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, flags,
@@ -171,11 +175,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], M: int,
 
 
 def attention(qkv: torch.Tensor, row_map: Optional[torch.Tensor], B: int, N_src: int, Np: int, C: int,
-              num_heads: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              num_heads: int, scale: float, out: Optional[torch.Tensor] = None, reverse: bool = False) -> torch.Tensor:
     """Attention over the Np kept tokens of each image, gather fused.  -> [B*Np, C] bf16"""
     out = torch.empty((B * Np, C), device=qkv.device, dtype=torch.bfloat16) if out is None else out
     _call("attention", 4.0 * B * Np * Np * C, _lib.load().rajni_attention_fwd,
-          qkv.data_ptr(), _ptr(row_map), out.data_ptr(), B, N_src, Np, C, num_heads, scale, _stream(qkv))
+          qkv.data_ptr(), _ptr(row_map), out.data_ptr(), B, N_src, Np, C, num_heads, scale, int(reverse), _stream(qkv))
     return out
 
 

@@ -15,6 +15,7 @@ Deliberate deviations from the reference:
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -181,6 +182,10 @@ class RAJNIViTWrapper(nn.Module):
         ops.gemm(ws["cols"], pe_w, pe_b, B * P, C, 768, residual=pos, ldres=C, res_row_map=ws["embed_pos_map"],
                  out=cur, ldd=C, out_row_map=ws["embed_out_map"], row_stats=stats, tag="embed")
 
+        # Zig-zag traversal: every persistent kernel walks its row tiles in the direction opposite to the kernel that
+        # produced its main operand, so it starts on the rows that kernel wrote last and that still sit in L2.
+        zig = os.environ.get("RAJNI_NO_ZIGZAG") is None       # A/B switch for profiling
+        rev = zig                      # the embed GEMM walked forward
         scores = None
         token_counts = []
         keep_log: List[Optional[torch.Tensor]] = []
@@ -195,7 +200,7 @@ class RAJNIViTWrapper(nn.Module):
             f2w, f2b = pk.linear(blk.mlp.fc2)
             hidden = f1w.shape[0]
             M = B * N
-            ops.gemm(cur, qw, qb, M, 3 * C, C, out=ws["qkv"], ln=(stats, slots, qsum, e1), tag="qkv")   # model.py:51 + attention.py:22
+            ops.gemm(cur, qw, qb, M, 3 * C, C, out=ws["qkv"], ln=(stats, slots, qsum, e1), tag="qkv", reverse=rev)   # model.py:51 + attention.py:22
             if blk.has_pruner:
                 attn: RAJNIAttention = blk.attn
                 keep = keep_count(N, attn.keep_ratio)                                 # attention.py:31-32
@@ -214,23 +219,24 @@ class RAJNIViTWrapper(nn.Module):
                                      keep_idx=keep_idx, next_scores=next_scores, row_map=row_map)
                 else:
                     ops.select(scores, keep, keep_idx=keep_idx, next_scores=next_scores, row_map=row_map)
-                ops.attention(ws["qkv"], row_map, B, N, Np, C, H, float(attn.scale), out=ws["att"])
+                ops.attention(ws["qkv"], row_map, B, N, Np, C, H, float(attn.scale), out=ws["att"], reverse=zig and not rev)
                 # proj + gathered residual: x_new[b,j] = x[b, keep_idx[b,j]] + proj(att)   model.py:55-58
                 ops.gemm(ws["att"], pw, pb, B * Np, C, C, residual=cur, ldres=C, res_row_map=row_map, out=nxt, ldd=C,
-                         row_stats=stats, tag="proj")
+                         row_stats=stats, tag="proj", reverse=rev)
                 cur, nxt = nxt, cur
                 scores = next_scores                                                  # attention.py:58
                 keep_log.append(keep_idx)
                 N = Np
                 M = B * N
             else:
-                ops.attention(ws["qkv"], None, B, N, N, C, H, float(blk.attn.scale), out=ws["att"])
-                ops.gemm(ws["att"], pw, pb, M, C, C, residual=cur, ldres=C, out=cur, ldd=C, row_stats=stats, tag="proj")   # in place
+                ops.attention(ws["qkv"], None, B, N, N, C, H, float(blk.attn.scale), out=ws["att"], reverse=zig and not rev)
+                ops.gemm(ws["att"], pw, pb, M, C, C, residual=cur, ldres=C, out=cur, ldd=C, row_stats=stats, tag="proj", reverse=rev)   # in place
                 scores = None                                                         # model.py:63
                 keep_log.append(None)
             ops.gemm(cur, f1w, f1b, M, hidden, C, gelu=True, out=ws["hid"], ldd=hidden,
-                     ln=(stats, slots, f1sum, e2), tag="fc1")                                    # model.py:59 (norm2 + fc1 + GELU)
-            ops.gemm(ws["hid"], f2w, f2b, M, C, hidden, residual=cur, ldres=C, out=cur, ldd=C, row_stats=stats, tag="fc2")
+                     ln=(stats, slots, f1sum, e2), tag="fc1", reverse=zig and not rev)                                    # model.py:59 (norm2 + fc1 + GELU)
+            ops.gemm(ws["hid"], f2w, f2b, M, C, hidden, residual=cur, ldres=C, out=cur, ldd=C, row_stats=stats, tag="fc2", reverse=rev)
+            rev = zig and not rev
 
         # ---- final norm on the CLS rows only (LayerNorm is row-wise) + head   model.py:65-66
         gn, bn, en = pk.norm(m.norm)

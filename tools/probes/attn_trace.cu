@@ -17,7 +17,7 @@ int main(int argc, char** argv) {
     cudaMalloc(&qkv, h.size() * 2); cudaMalloc(&out, (size_t)B * Np * C * 2); cudaMalloc(&rmap, rm.size() * 4);
     cudaMemcpy(qkv, h.data(), h.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(rmap, rm.data(), rm.size() * 4, cudaMemcpyHostToDevice);
-    for (int i = 0; i < 3; ++i) rajni::launch_attention_tc(qkv, Np < N ? rmap : nullptr, out, B, N, Np, C, H, 0.125f, 0);
+    for (int i = 0; i < 3; ++i) rajni::launch_attention_tc(qkv, Np < N ? rmap : nullptr, out, B, N, Np, C, H, 0.125f, 0, 0);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
     static long long tr[64 * 32];
