@@ -16,7 +16,7 @@ import pytest
 import torch
 
 from oracle import rajni_oracle as orc
-from tests.cases import E2E_CASES, MICRO_SCHEDULE, README_SCHEDULE, C3_SCHEDULE, make_images, npz
+from tests.cases import E2E_CASES, MICRO_SCHEDULE, README_SCHEDULE, C3_SCHEDULE, C4_SCHEDULE, make_images, npz
 from tests.conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
@@ -161,10 +161,12 @@ def near_tie_mismatch(ours: torch.Tensor, ref_scores: torch.Tensor, keep: int, r
     return overlap / B, worst
 
 
-@pytest.mark.parametrize("name,sched,batch", [("vit_base_patch16_224", README_SCHEDULE, 16),
-                                              ("vit_small_patch16_224", C3_SCHEDULE, 16)])
-def test_forward_vs_oracle_full_models(pkg, name, sched, batch):
-    """BASELINE configs 2 and 3 at a batch the CPU oracle finishes in seconds.
+@pytest.mark.parametrize("name,sched,batch,size", [("vit_base_patch16_224", README_SCHEDULE, 16, 224),
+                                                   ("vit_small_patch16_224", C3_SCHEDULE, 16, 224),
+                                                   ("vit_large_patch16_224", C4_SCHEDULE, 4, 224),
+                                                   ("deit_base_patch16_384", README_SCHEDULE, 4, 384)])
+def test_forward_vs_oracle_full_models(pkg, name, sched, batch, size):
+    """BASELINE configs 2, 3, 4 (24 pruned blocks, C=1024) and 5 (577 tokens) at a batch the CPU oracle finishes in seconds.
 
     End-to-end drift on random-init weights is dominated by selection noise (the reference's own
     fp32-vs-bf16 runs diverge the same way), so the comparison is teacher-forced:
@@ -177,7 +179,7 @@ def test_forward_vs_oracle_full_models(pkg, name, sched, batch):
     base = create_model(name, seed=0)
     params = orc.extract_params(copy.deepcopy(base))
     model = pkg.RAJNIViTWrapper(base, sched).cuda().eval()
-    images = make_images(batch, 224, 1234)
+    images = make_images(batch, size, 1234)
     logits = model(images.cuda()).cpu()
     ours = [None if k is None else k.cpu().long() for k in model._last_keep_idx]
     for k in ours:
