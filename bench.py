@@ -259,9 +259,17 @@ def main():
                 gemm[k] += v[k]
     gemm_tflops = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] else 0.0
     peak_tf = pk["bf16_tflops_sustained"]
+    traffic, traffic_src = None, None
+    try:                               # ncu dram bytes per GEMM launch, captured once per round (bench.py cannot run ncu itself)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["gemm"]
+        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all GEMM launches of a step)",
                 "achieved": round(gemm_tflops, 1), "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": round(gemm_tflops / peak_tf, 4), "traffic": None, "peak_source": pk["source"] + " sustained",
+                "frac": round(gemm_tflops / peak_tf, 4), "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                "traffic_source": traffic_src, "flop_per_launch": round(gemm["work"] / max(gemm["launches"], 1), 1),
+                "peak_source": pk["source"] + " sustained",
                 "launches_per_step": gemm["launches"], "ms_per_step": round(gemm["ms"], 3)}
     step_ms = sum(v["ms"] for v in prof.values())
     kernels = {}
