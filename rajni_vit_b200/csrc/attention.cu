@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const AttnParams
 
 int launch_attention_tc(const void* qkv, const int32_t* row_map, void* out, int B, int N_src, int Np,
                         int C, int H, float scale, int reverse, cudaStream_t stream);   // attention_tc.cu
+int launch_attention_long(const void* qkv, const int32_t* row_map, void* out, int B, int N_src, int Np,
+                          int C, int H, float scale, int reverse, cudaStream_t stream);  // attention_long.cu
 
 }  // namespace rajni
 
@@ -207,11 +209,13 @@ extern "C" int rajni_attention_fwd(const void* qkv, const int32_t* row_map, void
                   "rajni_attention_fwd: B=%d N_src=%d Np=%d C=%d H=%d (head dim must be 64)", B, N_src, Np, C, H);
     RAJNI_REQUIRE(row_map || N_src == Np, RAJNI_EINVAL, "rajni_attention_fwd: N_src != Np needs a row_map");
     RAJNI_REQUIRE(B <= 65535 && H <= 65535, RAJNI_EINVAL, "rajni_attention_fwd: B or H exceeds grid limits");
-    // tcgen05 kernel for sequences that fit one TMEM score tile (every 224-px config); the mma.sync
-    // kernel below covers longer sequences (577-token config) until the multi-block version lands.
+    // tcgen05 kernels: attention_tc for sequences that fit one TMEM score tile (every 224-px config), attention_long
+    // (key blocks, two passes) for longer ones (the 577-token config).  RAJNI_ATTN_LEGACY=1 selects the round-1
+    // mma.sync kernel below instead (kept for A/B timing and as an independent implementation for the tests).
     static const bool legacy = getenv("RAJNI_ATTN_LEGACY") != nullptr;
     if (!legacy) {
-        int rc = launch_attention_tc(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, static_cast<cudaStream_t>(stream));
+        int rc = Np <= 256 ? launch_attention_tc(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, static_cast<cudaStream_t>(stream))
+                           : launch_attention_long(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, static_cast<cudaStream_t>(stream));
         if (rc != 0) return rc < 0 ? rc : RAJNI_OK;
     }
     AttnParams p{};

@@ -174,10 +174,22 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], M: int,
     return out
 
 
+LONG_SEQ = 256          # above this many kept tokens the key-block kernel runs; it wants its rows compacted first
+
+
 def attention(qkv: torch.Tensor, row_map: Optional[torch.Tensor], B: int, N_src: int, Np: int, C: int,
-              num_heads: int, scale: float, out: Optional[torch.Tensor] = None, reverse: bool = False) -> torch.Tensor:
-    """Attention over the Np kept tokens of each image, gather fused.  -> [B*Np, C] bf16"""
+              num_heads: int, scale: float, out: Optional[torch.Tensor] = None, reverse: bool = False,
+              compact: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Attention over the Np kept tokens of each image.  -> [B*Np, C] bf16
+
+    Np <= 256: the kept-token gather is fused into the kernel's loads (cp.async by row index).
+    Np  > 256: the key-block kernel streams K/V blocks with TMA, which needs consecutive rows, so the kept rows are
+    compacted once with ``gather_rows`` (HBM-bound, into ``compact`` [B*Np, 3C] if given) and the dense path runs on them:
+    per-row cp.async sustains only ~8 B/clk/SM, TMA boxes are not limited that way (profiles/r1_attn_long.txt)."""
     out = torch.empty((B * Np, C), device=qkv.device, dtype=torch.bfloat16) if out is None else out
+    if row_map is not None and Np > LONG_SEQ:
+        qkv = gather_rows(qkv.view(-1, 3 * C), row_map, out=None if compact is None else compact[: B * Np])
+        row_map, N_src = None, Np
     _call("attention", 4.0 * B * Np * Np * C, _lib.load().rajni_attention_fwd,
           qkv.data_ptr(), _ptr(row_map), out.data_ptr(), B, N_src, Np, C, num_heads, scale, int(reverse), _stream(qkv))
     return out

@@ -219,7 +219,10 @@ class RAJNIViTWrapper(nn.Module):
                                      keep_idx=keep_idx, next_scores=next_scores, row_map=row_map)
                 else:
                     ops.select(scores, keep, keep_idx=keep_idx, next_scores=next_scores, row_map=row_map)
-                ops.attention(ws["qkv"], row_map, B, N, Np, C, H, float(attn.scale), out=ws["att"], reverse=zig and not rev)
+                if Np > ops.LONG_SEQ and "qkvc" not in ws:                             # compaction buffer, long sequences only
+                    ws["qkvc"] = torch.empty((B * ws["N0"], 3 * C), device=x.device, dtype=torch.bfloat16)
+                ops.attention(ws["qkv"], row_map, B, N, Np, C, H, float(attn.scale), out=ws["att"], reverse=zig and not rev,
+                              compact=ws.get("qkvc"))
                 # proj + gathered residual: x_new[b,j] = x[b, keep_idx[b,j]] + proj(att)   model.py:55-58
                 ops.gemm(ws["att"], pw, pb, B * Np, C, C, residual=cur, ldres=C, res_row_map=row_map, out=nxt, ldd=C,
                          row_stats=stats, tag="proj", reverse=rev)
