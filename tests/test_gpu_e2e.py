@@ -228,3 +228,18 @@ def test_evaluate_model(pkg):
     params = orc.extract_params(copy.deepcopy(model.m).cpu().float())
     ref_acc, _ = orc.evaluate(params, MICRO_SCHEDULE, data, warmup=0)
     print("acc", acc2, "oracle acc", ref_acc)
+
+
+def test_cli_synthetic(pkg, tmp_path, capsys):
+    """python -m rajni_vit_b200.run with the reference's flags on synthetic batches: string-key schedule JSON prunes
+    (normalised), --compare_base runs the un-pruned model on the same kernels."""
+    import json
+    from rajni_vit_b200 import run
+    sched = tmp_path / "schedule.json"
+    sched.write_text(json.dumps({"3": {"keep_ratio": 0.95, "update": False}, "4": {"keep_ratio": 0.95, "update": True},
+                                 "5": {"keep_ratio": 0.85, "update": True}}))
+    res = run.main(["--synthetic", "3", "--batch_size", "8", "--model", "vit_tiny_patch16_224", "--schedule", str(sched),
+                    "--warmup", "1", "--compare_base"])
+    out = capsys.readouterr().out
+    assert "token_counts [197, 197, 197, 197, 187, 177" in out and "speed-up" in out
+    assert res["base"][1] > 0 and res["rajni"][1] > 0

@@ -158,3 +158,24 @@ def test_evaluate_model_data_parallel_gloo(tmp_path):
     got = json.load(open(out))
     assert got["acc"] == pytest.approx(acc1, abs=1e-9)
     assert got["ips"] > 0
+
+
+def test_cli_flags_match_reference():
+    """Same flags and defaults as rajni/run.py:17-43 (plus --synthetic); a schedule is mandatory (run.py:115-116)."""
+    from rajni_vit_b200 import run
+    a = run.get_args(["--data_path", "/x", "--schedule", "s.json", "--compare_base", "--max_batches", "3"])
+    assert (a.batch_size, a.num_workers, a.pin_mem, a.model, a.device, a.warmup) == (256, 8, True, "vit_base_patch16_224", "cuda", 5)
+    assert a.compare_base and a.max_batches == 3 and a.schedule == "s.json"
+    with pytest.raises(SystemExit):
+        run.get_args(["--schedule", "s.json"])                  # neither --data_path nor --synthetic
+
+
+def test_standin_state_dict_uses_timm_names():
+    """A timm checkpoint must load into the stand-in by name: same keys, same shapes."""
+    from rajni_vit_b200.vit import create_model
+    sd = create_model("vit_tiny_patch16_224", seed=0).state_dict()
+    for k, shape in {"cls_token": (1, 1, 192), "pos_embed": (1, 197, 192), "patch_embed.proj.weight": (192, 3, 16, 16),
+                     "blocks.0.norm1.weight": (192,), "blocks.0.attn.qkv.weight": (576, 192), "blocks.0.attn.qkv.bias": (576,),
+                     "blocks.0.attn.proj.weight": (192, 192), "blocks.11.mlp.fc1.weight": (768, 192),
+                     "blocks.11.mlp.fc2.bias": (192,), "norm.weight": (192,), "head.weight": (1000, 192)}.items():
+        assert tuple(sd[k].shape) == shape, k
