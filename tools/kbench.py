@@ -19,7 +19,9 @@ except Exception:
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
 
-def timeit(fn, iters=10, warm=3):
+def timeit(fn, iters=10, warm=3, inner=1):
+    """Median over `iters` of the time of `inner` back-to-back calls (L2 flushed before each group).  The event timer on
+    these boxes ticks in ~4 us steps, so kernels shorter than ~100 us should be timed with inner > 1."""
     for _ in range(warm):
         fn()
     ts = []
@@ -27,10 +29,11 @@ def timeit(fn, iters=10, warm=3):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for _ in range(inner):
+            fn()
         b.record()
         torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
+        ts.append(a.elapsed_time(b) / inner)
     ts.sort()
     return ts[len(ts) // 2] * 1e-3
 
@@ -66,7 +69,7 @@ def main():
     # score+select
     for N, keep in ((197, 172), (173, 151), (152, 120), (121, 86)) if want("score") else ():
         qkv = torch.randn(B, N, 2304, device="cuda").bfloat16()
-        t = timeit(lambda: ops.score_select(qkv, 12, keep))
+        t = timeit(lambda: ops.score_select(qkv, 12, keep), inner=8)
         nbytes = B * (2 * N * 768 * 2 + 768 * 2 + 8 * (keep + 1))
         print(f"score_select N={N:3d}            {t*1e6:8.1f} us  {nbytes/t/1e9:7.1f} GB/s ({nbytes/t/1e9/PEAKS['hbm_gbs']*100:5.1f}% of measured HBM)")
     # attention
