@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "librajni_b200.so")
 
 RAJNI_OK, RAJNI_EINVAL, RAJNI_ECUDA, RAJNI_EARCH, RAJNI_ERANGE = 0, -1, -2, -3, -4
 EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32, EPI_LN_FOLD, EPI_ROW_STATS, HINT_REVERSE_M = 1, 2, 4, 8, 16, 32, 64
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class GemmArgs(Structure):

@@ -25,7 +25,7 @@
 // LayerNorm folding (model.py:51,59): LN(x) W^T = rstd*(x (W.gamma)^T - mean * wsum) + W beta, so the
 // normalised activations are never materialised: the GEMM that PRODUCES x (proj / fc2 / patch-embed
 // epilogue) also emits per-row partial (sum, sum of squares) of the bf16 values it stores, one slot
-// per (n-tile, column half); the GEMM that CONSUMES LN(x) (qkv / fc1) runs on x itself with
+// per 32-column chunk; the GEMM that CONSUMES LN(x) (qkv / fc1) runs on x itself with
 // gamma-scaled weights and applies  acc*rstd + (-mean*rstd)*wsum[n] + bias'[n]  in its epilogue.
 #include <cuda.h>
 #include <cstdlib>
@@ -51,7 +51,7 @@ template <int BN, int CG> struct GemmCfg {
     static constexpr int kBBytes = kBRows * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (192 * 1024) / kStageBytes;
-    static constexpr int kTmemCols = 2 * BN;                // double-buffered accumulator
+    static constexpr int kTmemCols = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // double-buffered accumulator, power of 2
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 256 /*barriers*/ + 1024 /*align*/;
 };
 
@@ -71,7 +71,7 @@ struct GemmParams {
     long long ln_stats_ld;
     int ln_slots;
     float ln_inv_k, ln_eps;
-    float2* row_stats;          // [tiles_n*2][row_stats_ld] partial (sum, sumsq) of the rows of D, or null
+    float2* row_stats;          // [N/32][row_stats_ld] partial (sum, sumsq) of the rows of D per 32-column chunk, or null
     long long row_stats_ld;
 };
 
@@ -300,7 +300,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     rstd2 = f2pack(rstd, rstd);
                     mr2 = f2pack(-mean * rstd, -mean * rstd);
                 }
-                uint64_t sum2 = 0, sq2 = 0;                  // (0.f, 0.f)
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
@@ -323,6 +322,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                     }
                     uint32_t o[16];
+                    uint64_t sum2 = 0, sq2 = 0;                  // (0.f, 0.f): statistics of this 32-column chunk
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 bv = lds128(sb + (ch * 32 + j) * 4);
@@ -362,13 +362,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (valid) {
                         stg256(dptr + ch * 32, *reinterpret_cast<uint32_t(*)[8]>(&o[0]));
                         stg256(dptr + ch * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&o[8]));
+                        if (kRes && p.row_stats != nullptr) {
+                            // one slot per 32-column chunk of the row, whatever the tile width: the partition (and so the
+                            // rounding of the LayerNorm statistics) does not depend on the batch size
+                            float a0, a1, b0, b1;
+                            f2unpack(sum2, a0, a1);
+                            f2unpack(sq2, b0, b1);
+                            p.row_stats[(long long)((ncol0 >> 5) + ch) * p.row_stats_ld + orow] = make_float2(a0 + a1, b0 + b1);
+                        }
                     }
-                }
-                if (kRes && p.row_stats != nullptr && valid) {
-                    float a0, a1, b0, b1;
-                    f2unpack(sum2, a0, a1);
-                    f2unpack(sq2, b0, b1);
-                    p.row_stats[(long long)(n_blk * 2 + half) * p.row_stats_ld + orow] = make_float2(a0 + a1, b0 + b1);
                 }
             }
         } else {
@@ -588,10 +590,26 @@ static int launch_gemm(const void* A, const void* W, GemmParams& p, cudaStream_t
     return launch_gemm_mode<BN, CG, MODE_GENERIC, false>(A, W, p, stream);
 }
 
-// tile width: minimise padded columns; the 64-wide tile runs at ~2/3 rate (shared-memory bound).
-// `exact` (LN_FOLD / ROW_STATS epilogues, which have no column-tail path): the widest tile that divides N.
-static int pick_bn(int N, bool exact) {
-    if (exact) return N % 256 == 0 ? 256 : N % 128 == 0 ? 128 : 64;
+// Tile width.  Generic epilogue: minimise padded columns (the 64-wide tile runs at ~2/3 rate, shared-memory bound).
+// `exact` (hot epilogues, no column-tail path): among the widths that divide N, the CTA-pair tiles (256 or 192 wide,
+// 256 rows) are preferred; between those two the one with fewer, fuller waves over the 74 CTA pairs wins
+// (e.g. N = 768, M = 44288: 173 x 3 tiles of 256 = 7.01 waves -> 8, but 173 x 4 tiles of 192 = 9.35 -> 10 x 3/4 = 7.5).
+static int pick_bn(int N, int M, bool exact) {
+    if (exact) {
+        const bool pair = M > BM;
+        int best = 0;
+        double best_cost = 0;
+        for (int bn : {256, 192}) {
+            if (!pair || N % bn) continue;
+            const long long tiles = (long long)((M + 2 * BM - 1) / (2 * BM)) * (N / bn);
+            const int pairs = num_sms() / 2;
+            // the 192-wide tile re-reads A once more per row block: it has to save 8 % of the wave time to be chosen
+            const double cost = (double)((tiles + pairs - 1) / pairs) * bn * (bn == 192 ? 1.08 : 1.0);
+            if (!best || cost < best_cost) { best = bn; best_cost = cost; }
+        }
+        if (best) return best;
+        return N % 256 == 0 ? 256 : N % 128 == 0 ? 128 : 64;
+    }
     auto cost = [&](int bn) { long long padded = (long long)((N + bn - 1) / bn) * bn; return bn == 64 ? padded * 3 / 2 : padded; };
     int bn = 256;
     if (cost(128) < cost(bn)) bn = 128;
@@ -604,9 +622,8 @@ static int pick_bn(int N, bool exact) {
 using namespace rajni;
 
 extern "C" int rajni_gemm_row_stats_slots(int N) {
-    if (N <= 0) return 0;
-    if (N % 64 != 0) return 0;                      // ROW_STATS needs whole tiles
-    return 2 * (N / pick_bn(N, true));
+    if (N <= 0 || N % 64 != 0) return 0;            // ROW_STATS needs whole tiles
+    return N / 32;                                  // one slot per 32-column chunk
 }
 
 extern "C" int rajni_gemm_bf16_ex(const rajni_gemm_args* a, void* stream) {
@@ -641,12 +658,13 @@ extern "C" int rajni_gemm_bf16_ex(const rajni_gemm_args* a, void* stream) {
     p.row_stats_ld = a->row_stats_ld;
     const bool exact = (flags & (RAJNI_EPI_LN_FOLD | RAJNI_EPI_ROW_STATS)) != 0;
     RAJNI_REQUIRE(!exact || N % 64 == 0, RAJNI_EINVAL, "rajni_gemm_bf16: LN_FOLD / ROW_STATS need N %% 64 == 0 (N=%d)", N);
-    const int bn = pick_bn(N, exact);
+    const int bn = pick_bn(N, M, exact);
     auto s = static_cast<cudaStream_t>(stream);
     // wide problems run as CTA pairs (256 x 256 tiles); narrow ones keep single-CTA tiles
     static const bool force_cg1 = getenv("RAJNI_GEMM_CG1") != nullptr;     // debugging aid
     switch (bn) {
         case 256: return (M > BM && !force_cg1) ? launch_gemm<256, 2>(a->A, a->W, p, s) : launch_gemm<256, 1>(a->A, a->W, p, s);
+        case 192: return launch_gemm<192, 2>(a->A, a->W, p, s);
         case 128: return launch_gemm<128, 1>(a->A, a->W, p, s);
         default: return launch_gemm<64, 1>(a->A, a->W, p, s);
     }

@@ -138,7 +138,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 
 def row_stats_slots(n_cols: int) -> int:
-    """Partial-sum slots per row that a ``row_stats`` GEMM with ``n_cols`` output columns writes."""
+    """Partial-sum slots per row that a ``row_stats`` GEMM with ``n_cols`` output columns writes (one per 32 columns)."""
     return int(_lib.load().rajni_gemm_row_stats_slots(n_cols))
 
 

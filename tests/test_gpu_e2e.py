@@ -171,7 +171,8 @@ def test_forward_vs_oracle_full_models(pkg, name, sched, batch, size):
     End-to-end drift on random-init weights is dominated by selection noise (the reference's own
     fp32-vs-bf16 runs diverge the same way), so the comparison is teacher-forced:
       1. arithmetic: the oracle is run with OUR kept indices forced at every pruned block; logits must
-         agree within bf16 tolerance (max |dlogit| < 0.08 at logit std ~0.57, top-1 agreement >= 0.9);
+         agree within bf16 tolerance (max |dlogit| < 0.08 at logit std ~0.57; same top-1 wherever the oracle's
+         top-2 margin exceeds twice that error);
       2. selection: at every pruned block the oracle's own fp32 scores on that same input must rank
          our kept tokens identically except for tokens within 3 % of the cut score;
       3. token_counts exact.  The free-running comparison is printed for the record."""
@@ -191,7 +192,10 @@ def test_forward_vs_oracle_full_models(pkg, name, sched, batch, size):
     err = (logits - ref).abs().max().item()
     agree = (logits.argmax(1) == ref.argmax(1)).float().mean().item()
     print(f"{name} (selection teacher-forced): max |dlogit| {err:.4f}, top-1 agreement {agree:.3f}, logit std {ref.std():.3f}")
-    assert err < 0.08 and agree >= 0.9
+    # top-1 may only differ where the oracle's own top-2 margin is inside the logit error (random-init logits are nearly flat)
+    top2 = ref.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 2 * err
+    assert err < 0.08 and bool((logits.argmax(1) == ref.argmax(1))[decided].all())
     for rec, kidx in zip(trace, ours):
         if kidx is None:
             continue
