@@ -63,6 +63,8 @@ class RAJNIViTWrapper(nn.Module):
         self._last_keep_idx: List[Optional[torch.Tensor]] = []
         self._packs = PackCache()
         self._ws = {}
+        self._graphs = {}
+        self.use_cuda_graph = os.environ.get("RAJNI_CUDA_GRAPH", "") not in ("", "0")
         self._validate()
 
     # ------------------------------------------------------------------ contract checks
@@ -104,7 +106,12 @@ class RAJNIViTWrapper(nn.Module):
     def _apply(self, fn, *a, **kw):
         self._packs.clear()
         self._ws.clear()
+        self._graphs = {}
         return super()._apply(fn, *a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        self._graphs = {}
+        return super().load_state_dict(*a, **kw)
 
     def get_last_stats(self):
         return self._last_stats
@@ -146,6 +153,31 @@ class RAJNIViTWrapper(nn.Module):
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """model.py:30-69.  With ``use_cuda_graph`` (attribute, or RAJNI_CUDA_GRAPH=1 in the environment) the launch
+        sequence of a given input shape is captured once into a CUDA graph and replayed: the 68 launches of a step cost
+        ~13 us of host time each, which dominates small batches (vit_tiny at batch 8 is launch-bound).  Graph mode assumes
+        frozen weights; ``.to()`` / ``.bfloat16()`` / ``load_state_dict`` drop the captured graphs."""
+        if not self.use_cuda_graph or x.device.type != "cuda" or x.dim() != 4:
+            return self._forward_eager(x)
+        key = (tuple(x.shape), x.dtype, x.device)
+        entry = self._graphs.get(key)
+        if entry is None:
+            x_static = x.clone()
+            self._forward_eager(x_static)                       # builds packs and workspace, warms every kernel
+            torch.cuda.synchronize(x.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                y_static = self._forward_eager(x_static)
+            entry = (graph, x_static, y_static, self._last_stats, self._last_keep_idx)
+            self._graphs = {key: entry}                         # one shape resident, like the workspace
+        graph, x_static, y_static, stats, keep = entry
+        x_static.copy_(x)
+        graph.replay()
+        self._last_stats, self._last_keep_idx = stats, keep
+        return y_static.clone()
+
+    @torch.no_grad()
+    def _forward_eager(self, x: torch.Tensor) -> torch.Tensor:
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != x.shape[3] or x.shape[2] % 16:
             raise ValueError(f"expected images [B,3,S,S] with S a multiple of 16, got {tuple(x.shape)}")
         if x.device.type != "cuda":

@@ -16,7 +16,7 @@ import pytest
 import torch
 
 from oracle import rajni_oracle as orc
-from tests.cases import E2E_CASES, MICRO_SCHEDULE, README_SCHEDULE, C3_SCHEDULE, C4_SCHEDULE, make_images, npz
+from tests.cases import E2E_CASES, MICRO_SCHEDULE, README_SCHEDULE, C1_SCHEDULE, C3_SCHEDULE, C4_SCHEDULE, make_images, npz
 from tests.conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
@@ -247,3 +247,20 @@ def test_cli_synthetic(pkg, tmp_path, capsys):
     out = capsys.readouterr().out
     assert "token_counts [197, 197, 197, 197, 187, 177" in out and "speed-up" in out
     assert res["base"][1] > 0 and res["rajni"][1] > 0
+
+
+def test_cuda_graph_mode_matches_eager(pkg):
+    """Opt-in graph replay: bit-identical logits and the same stats as the eager launch sequence, across replays and
+    after a shape change."""
+    model = build(pkg, "vit_tiny_patch16_224", C1_SCHEDULE)
+    x1, x2 = make_images(8, 224, 7).cuda(), make_images(8, 224, 8).cuda()
+    ref1, ref2 = model(x1).clone(), model(x2).clone()
+    stats = model.get_last_stats()
+    model.use_cuda_graph = True
+    for _ in range(2):
+        assert torch.equal(model(x1), ref1) and torch.equal(model(x2), ref2)
+        assert model.get_last_stats() == stats
+    small = make_images(4, 224, 9).cuda()
+    y = model(small)
+    model.use_cuda_graph = False
+    assert torch.equal(y, model(small))

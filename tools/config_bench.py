@@ -21,6 +21,7 @@ for name, model_name, sched, B, S in CASES:
     if only and not any(o in name for o in only):
         continue
     m = RAJNIViTWrapper(create_model(model_name, seed=0), sched).cuda().eval()
+    m.use_cuda_graph = os.environ.get("RAJNI_CUDA_GRAPH", "") not in ("", "0")
     x = torch.randn(B, 3, S, S, device="cuda")
     for _ in range(5):
         m(x)
@@ -33,6 +34,7 @@ for name, model_name, sched, B, S in CASES:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
+    m.use_cuda_graph = False
     prof = ops.profile_steps(lambda: m(x), steps=2)
     top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:5]
     print(f"{name:40s} {ms:8.3f} ms/step {B / ms * 1e3:10.0f} img/s   " + "  ".join(f"{k}={v['ms']:.3f}" for k, v in top), flush=True)
