@@ -596,6 +596,8 @@ static int launch_gemm(const void* A, const void* W, GemmParams& p, cudaStream_t
 // (e.g. N = 768, M = 44288: 173 x 3 tiles of 256 = 7.01 waves -> 8, but 173 x 4 tiles of 192 = 9.35 -> 10 x 3/4 = 7.5).
 static int pick_bn(int N, int M, bool exact) {
     if (exact) {
+        static const char* force = getenv("RAJNI_GEMM_BN");                 // debugging aid: force 256 or 192 where it divides N
+        if (force && M > BM && N % atoi(force) == 0 && (atoi(force) == 256 || atoi(force) == 192)) return atoi(force);
         const bool pair = M > BM;
         int best = 0;
         double best_cost = 0;
