@@ -319,3 +319,23 @@ def test_patch_embed(ops, S, C, B):
     got = x.cpu().float()
     report("embed", got, ref)
     assert ((got - ref).abs() <= BF16_RTOL * ref.abs() + 4e-3).all()
+
+
+def test_reverse_traversal_hints_do_not_change_results(ops):
+    """RAJNI_HINT_REVERSE_M / rajni_attention_fwd(reverse=1) only change the order in which tiles are visited."""
+    g = torch.Generator().manual_seed(11)
+    M, N, K = 3000, 768, 768
+    a = dev(bf16_round(torch.randn(M, K, generator=g)), torch.bfloat16)
+    w = dev(bf16_round(torch.randn(N, K, generator=g) / math.sqrt(K)), torch.bfloat16)
+    bias = dev(torch.randn(N, generator=g))
+    res = dev(bf16_round(torch.randn(M, N, generator=g)), torch.bfloat16)
+    st0 = torch.zeros(ops.row_stats_slots(N), M, 2, device="cuda")
+    st1 = torch.zeros_like(st0)
+    y0 = ops.gemm(a, w, bias, M, N, K, residual=res, row_stats=st0)
+    y1 = ops.gemm(a, w, bias, M, N, K, residual=res, row_stats=st1, reverse=True)
+    assert torch.equal(y0, y1) and torch.equal(st0, st1)
+    for B, Nt, H in ((3, 197, 3), (2, 300, 2)):
+        qkv = dev(make_qkv(B, Nt, H, 64, 77), torch.bfloat16).view(B * Nt, 3 * H * 64)
+        o0 = ops.attention(qkv, None, B, Nt, Nt, H * 64, H, 0.125)
+        o1 = ops.attention(qkv, None, B, Nt, Nt, H * 64, H, 0.125, reverse=True)
+        assert torch.equal(o0, o1)
