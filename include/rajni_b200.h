@@ -21,13 +21,14 @@
 #ifndef RAJNI_B200_H
 #define RAJNI_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define RAJNI_ABI_VERSION 4
+#define RAJNI_ABI_VERSION 5
 
 enum {
     RAJNI_OK = 0,
@@ -75,6 +76,14 @@ int rajni_select(const float* scores, int B, int N, int keep,
 int rajni_score_select(const void* qkv, int B, int N, int C, int H, int keep, float eps,
                        float* scores, int32_t* keep_idx, float* next_scores,
                        int32_t* row_map, void* stream);
+
+/* Same result, bit for bit, in two launches for batches with far fewer images than the GPU has SMs (one CTA per image
+ * would leave most SMs idle): the K/V pass is spread over (image, 16-row block) CTAs into `workspace`
+ * (rajni_score_select_workspace_bytes(B,N,C,H) bytes, 16-byte aligned, caller-owned), then the per-image kernel finishes. */
+size_t rajni_score_select_workspace_bytes(int B, int N, int C, int H);
+int rajni_score_select_split(const void* qkv, int B, int N, int C, int H, int keep, float eps,
+                             float* scores, int32_t* keep_idx, float* next_scores, int32_t* row_map,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a3 / a9: row gather-compaction (attention.py:42-43, model.py:55-56)
  * dst[r, :] = src[row_map[r], :], rows of `row_elems` bf16 (multiple of 8). */

@@ -26,6 +26,8 @@ struct ScoreSelectParams {
     int32_t* keep_idx;          // [B,keep+1] or null (score-only)
     float* next_scores;         // [B,keep+1]
     int32_t* row_map;           // [B*(keep+1)] or null
+    const float* pre_logit;     // [B][H*N] CLS logits already computed by score_stream_kernel, or null
+    const float* pre_vm;        // [B][N*64] head-averaged value rows already computed, or null
     int N, C, H, keep;
     float eps;
 };
@@ -159,6 +161,88 @@ __device__ void select_and_emit(const float* score, uint32_t* s_hist, int* s_mis
     }
 }
 
+// One token row: CLS logits of every head (q pre-scaled) and the head-averaged value row.  Shared by the fused kernel
+// (destinations in shared memory) and the streaming kernel of the split path (destinations in global scratch), so both
+// paths produce bit-identical numbers.
+template <int CPL>
+__device__ __forceinline__ void score_row(const __nv_bfloat16* row, const float (&q)[CPL][8], int lane, int chunks, int C, int H,
+                                          int N, int n, float* logit_dst, float* vm_dst, float inv_h) {
+    uint4 kk[CPL], vv[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+        int j = lane + 32 * i;
+        bool ok = j < chunks;
+        kk[i] = ok ? ld_stream16(row + C + j * 8) : make_uint4(0, 0, 0, 0);
+        vv[i] = ok ? ld_stream16(row + 2 * C + j * 8) : make_uint4(0, 0, 0, 0);
+    }
+    float va[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+        float2 k0 = bf16x2_to_float2(kk[i].x), k1 = bf16x2_to_float2(kk[i].y);
+        float2 k2 = bf16x2_to_float2(kk[i].z), k3 = bf16x2_to_float2(kk[i].w);
+        float dot = q[i][0] * k0.x;
+        dot = fmaf(q[i][1], k0.y, dot); dot = fmaf(q[i][2], k1.x, dot); dot = fmaf(q[i][3], k1.y, dot);
+        dot = fmaf(q[i][4], k2.x, dot); dot = fmaf(q[i][5], k2.y, dot); dot = fmaf(q[i][6], k3.x, dot);
+        dot = fmaf(q[i][7], k3.y, dot);
+        // 8 lanes share a head (64 dims = 8 chunks)
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+        int h = (lane >> 3) + 4 * i;
+        if ((lane & 7) == 0 && h < H) logit_dst[(size_t)h * N + n] = dot;
+        float2 v0 = bf16x2_to_float2(vv[i].x), v1 = bf16x2_to_float2(vv[i].y);
+        float2 v2 = bf16x2_to_float2(vv[i].z), v3 = bf16x2_to_float2(vv[i].w);
+        va[0] += v0.x; va[1] += v0.y; va[2] += v1.x; va[3] += v1.y;
+        va[4] += v2.x; va[5] += v2.y; va[6] += v3.x; va[7] += v3.y;
+    }
+    // lanes l, l+8, l+16, l+24 hold the same 8 dims of different heads
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        va[e] += __shfl_xor_sync(0xffffffffu, va[e], 8);
+        va[e] += __shfl_xor_sync(0xffffffffu, va[e], 16);
+    }
+    if (lane < 8) {
+        float* dst = vm_dst + (size_t)n * kHeadDim + lane * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dst[e] = va[e] * inv_h;       // importance.py:24
+    }
+}
+
+// CLS query of the image, pre-scaled by 1/sqrt(64) (exact: power of two)
+template <int CPL>
+__device__ __forceinline__ void load_cls_query(const __nv_bfloat16* img, int lane, int chunks, float (&q)[CPL][8]) {
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+        int j = lane + 32 * i;
+        uint4 u = (j < chunks) ? ld_stream16(img + j * 8) : make_uint4(0, 0, 0, 0);
+        float2 a = bf16x2_to_float2(u.x), bb = bf16x2_to_float2(u.y), c = bf16x2_to_float2(u.z), d = bf16x2_to_float2(u.w);
+        q[i][0] = a.x * 0.125f; q[i][1] = a.y * 0.125f; q[i][2] = bb.x * 0.125f; q[i][3] = bb.y * 0.125f;
+        q[i][4] = c.x * 0.125f; q[i][5] = c.y * 0.125f; q[i][6] = d.x * 0.125f; q[i][7] = d.y * 0.125f;
+    }
+}
+
+// Split path, kernel 1: when a batch has far fewer images than the GPU has SMs (vit_large at 32 images per GPU), one CTA
+// per image leaves most SMs idle and each CTA latency-bound.  This kernel spreads the K/V pass over (image, 16-row block)
+// CTAs and leaves the per-token results in global scratch; score_select_kernel then starts from them (pre_logit / pre_vm).
+constexpr int kStreamThreads = 256;
+constexpr int kStreamRows = 16;
+template <int CPL>
+__global__ void __launch_bounds__(kStreamThreads) score_stream_kernel(const __nv_bfloat16* qkv, float* logit_g, float* vm_g,
+                                                                      int N, int C, int H) {
+    griddep_launch();
+    griddep_wait();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, chunks = C >> 3;
+    const __nv_bfloat16* img = qkv + (size_t)b * N * 3 * C;
+    float q[CPL][8];
+    load_cls_query<CPL>(img, lane, chunks, q);
+    const float inv_h = 1.0f / (float)H;
+    float* logit_dst = logit_g + (size_t)b * ((H * N + 3) & ~3);     // per-image stride padded to 16 bytes
+    float* vm_dst = vm_g + (size_t)b * N * kHeadDim;
+    for (int n = blockIdx.x * kStreamRows + warp; n < min(N, (int)(blockIdx.x + 1) * kStreamRows); n += kStreamThreads / 32)
+        score_row<CPL>(img + (size_t)n * 3 * C, q, lane, chunks, C, H, N, n, logit_dst, vm_dst, inv_h);
+}
+
 // CPL = 16-byte chunks per lane per plane = ceil(C / 256).
 // 64 registers per thread so that two CTAs (two images) share an SM: with one CTA per SM the 256 images of a batch
 // ran as two latency-bound waves on 148 SMs (57 us at N=197); resident together they take 45 us.
@@ -186,60 +270,28 @@ __global__ void __launch_bounds__(kSelThreads, 2) score_select_kernel(const Scor
     if (p.qkv != nullptr) {
         const int chunks = C >> 3;                 // 16-byte chunks per plane row
         const __nv_bfloat16* img = p.qkv + (size_t)b * N * 3 * C;
-        // CLS query, pre-scaled by 1/sqrt(64) (exact: power of two)
-        float q[CPL][8];
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) {
-            int j = lane + 32 * i;
-            uint4 u = (j < chunks) ? ld_stream16(img + j * 8) : make_uint4(0, 0, 0, 0);
-            float2 a = bf16x2_to_float2(u.x), bb = bf16x2_to_float2(u.y), c = bf16x2_to_float2(u.z), d = bf16x2_to_float2(u.w);
-            q[i][0] = a.x * 0.125f; q[i][1] = a.y * 0.125f; q[i][2] = bb.x * 0.125f; q[i][3] = bb.y * 0.125f;
-            q[i][4] = c.x * 0.125f; q[i][5] = c.y * 0.125f; q[i][6] = d.x * 0.125f; q[i][7] = d.y * 0.125f;
-        }
         const float inv_h = 1.0f / (float)H;
-        // ---- the single HBM pass: one warp per token row, K plane then V plane
+        if (p.pre_logit != nullptr) {
+            // split path: the K/V pass already ran (score_stream_kernel); fetch its per-token results (L2-resident)
+            const float* gl1 = p.pre_logit + (size_t)b * ((H * N + 3) & ~3);
+            const float4* gl = reinterpret_cast<const float4*>(gl1);
+            const float4* gv = reinterpret_cast<const float4*>(p.pre_vm + (size_t)b * N * kHeadDim);
+            for (int i = tid; i < (H * N) / 4; i += kSelThreads) {
+                const float4 v = __ldg(gl + i);
+                s_logit[4 * i] = v.x; s_logit[4 * i + 1] = v.y; s_logit[4 * i + 2] = v.z; s_logit[4 * i + 3] = v.w;
+            }
+            for (int i = ((H * N) / 4) * 4 + tid; i < H * N; i += kSelThreads) s_logit[i] = __ldg(gl1 + i);
+            for (int i = tid; i < N * kHeadDim / 4; i += kSelThreads) {
+                const float4 v = __ldg(gv + i);
+                s_vm[4 * i] = v.x; s_vm[4 * i + 1] = v.y; s_vm[4 * i + 2] = v.z; s_vm[4 * i + 3] = v.w;
+            }
+        } else {
+            float q[CPL][8];
+            load_cls_query<CPL>(img, lane, chunks, q);
+            // ---- the single HBM pass: one warp per token row, K plane then V plane
 #pragma unroll 2
-        for (int n = warp; n < N; n += kSelWarps) {
-            const __nv_bfloat16* row = img + (size_t)n * 3 * C;
-            uint4 kk[CPL], vv[CPL];
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                int j = lane + 32 * i;
-                bool ok = j < chunks;
-                kk[i] = ok ? ld_stream16(row + C + j * 8) : make_uint4(0, 0, 0, 0);
-                vv[i] = ok ? ld_stream16(row + 2 * C + j * 8) : make_uint4(0, 0, 0, 0);
-            }
-            float va[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                float2 k0 = bf16x2_to_float2(kk[i].x), k1 = bf16x2_to_float2(kk[i].y);
-                float2 k2 = bf16x2_to_float2(kk[i].z), k3 = bf16x2_to_float2(kk[i].w);
-                float dot = q[i][0] * k0.x;
-                dot = fmaf(q[i][1], k0.y, dot); dot = fmaf(q[i][2], k1.x, dot); dot = fmaf(q[i][3], k1.y, dot);
-                dot = fmaf(q[i][4], k2.x, dot); dot = fmaf(q[i][5], k2.y, dot); dot = fmaf(q[i][6], k3.x, dot);
-                dot = fmaf(q[i][7], k3.y, dot);
-                // 8 lanes share a head (64 dims = 8 chunks)
-                dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-                dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-                dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-                int h = (lane >> 3) + 4 * i;
-                if ((lane & 7) == 0 && h < H) s_logit[(size_t)h * N + n] = dot;
-                float2 v0 = bf16x2_to_float2(vv[i].x), v1 = bf16x2_to_float2(vv[i].y);
-                float2 v2 = bf16x2_to_float2(vv[i].z), v3 = bf16x2_to_float2(vv[i].w);
-                va[0] += v0.x; va[1] += v0.y; va[2] += v1.x; va[3] += v1.y;
-                va[4] += v2.x; va[5] += v2.y; va[6] += v3.x; va[7] += v3.y;
-            }
-            // lanes l, l+8, l+16, l+24 hold the same 8 dims of different heads
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                va[e] += __shfl_xor_sync(0xffffffffu, va[e], 8);
-                va[e] += __shfl_xor_sync(0xffffffffu, va[e], 16);
-            }
-            if (lane < 8) {
-                float* dst = s_vm + (size_t)n * kHeadDim + lane * 8;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) dst[e] = va[e] * inv_h;       // importance.py:24
-            }
+            for (int n = warp; n < N; n += kSelWarps)
+                score_row<CPL>(img + (size_t)n * 3 * C, q, lane, chunks, C, H, N, n, s_logit, s_vm, inv_h);
         }
         __syncthreads();
 
@@ -332,6 +384,29 @@ static int launch_score_select(const ScoreSelectParams& p, int B, cudaStream_t s
     return check_launch("score_select");
 }
 
+static size_t split_workspace_floats(int B, int N, int H) {
+    return (size_t)B * (((size_t)H * N + 3) & ~(size_t)3) + (size_t)B * N * kHeadDim;
+}
+
+// split path, kernel 1 (see score_stream_kernel)
+static int launch_score_stream(const __nv_bfloat16* qkv, int B, int N, int C, int H, float* ws, cudaStream_t stream) {
+    float* logit_g = ws;
+    float* vm_g = ws + (size_t)B * (((size_t)H * N + 3) & ~(size_t)3);
+    void (*kern)(const __nv_bfloat16*, float*, float*, int, int, int) = nullptr;
+    switch ((C + 255) / 256) {
+        case 1: kern = score_stream_kernel<1>; break;
+        case 2: kern = score_stream_kernel<2>; break;
+        case 3: kern = score_stream_kernel<3>; break;
+        case 4: kern = score_stream_kernel<4>; break;
+        default: RAJNI_REQUIRE(false, RAJNI_EINVAL, "score_select: C=%d > 1024 unsupported", C);
+    }
+    cudaError_t e = launch_kernel(kern, dim3((N + kStreamRows - 1) / kStreamRows, B), dim3(kStreamThreads), 0, stream, 1,
+                                  qkv, logit_g, vm_g, N, C, H);
+    count_launch();
+    RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "score_stream: launch failed: %s", cudaGetErrorString(e));
+    return check_launch("score_stream");
+}
+
 static int check_score_shape(int B, int N, int C, int H) {
     RAJNI_REQUIRE(B > 0 && N >= 2 && N <= 4096, RAJNI_EINVAL, "score: bad B=%d N=%d", B, N);
     RAJNI_REQUIRE(H > 0 && C == H * kHeadDim, RAJNI_EINVAL, "score: head dim must be 64 (C=%d H=%d)", C, H);
@@ -379,4 +454,33 @@ extern "C" int rajni_score_select(const void* qkv, int B, int N, int C, int H, i
     p.keep_idx = keep_idx; p.next_scores = next_scores; p.row_map = row_map;
     p.N = N; p.C = C; p.H = H; p.keep = keep; p.eps = eps;
     return launch_score_select(p, B, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t rajni_score_select_workspace_bytes(int B, int N, int C, int H) {
+    (void)C;
+    if (B <= 0 || N <= 0 || H <= 0) return 0;
+    return split_workspace_floats(B, N, H) * sizeof(float);
+}
+
+extern "C" int rajni_score_select_split(const void* qkv, int B, int N, int C, int H, int keep, float eps,
+                                        float* scores, int32_t* keep_idx, float* next_scores, int32_t* row_map,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+    RAJNI_REQUIRE(qkv && keep_idx && next_scores && workspace, RAJNI_EINVAL, "rajni_score_select_split: null pointer");
+    if (int rc = check_score_shape(B, N, C, H)) return rc;
+    RAJNI_REQUIRE(keep >= 1, RAJNI_EINVAL, "rajni_score_select_split: keep=%d < 1", keep);
+    RAJNI_REQUIRE(keep <= N - 1, RAJNI_ERANGE, "selected index k out of range (keep=%d, patches=%d)", keep, N - 1);
+    RAJNI_REQUIRE(B <= 65535, RAJNI_EINVAL, "rajni_score_select_split: B=%d exceeds the grid limit", B);
+    RAJNI_REQUIRE(workspace_bytes >= rajni_score_select_workspace_bytes(B, N, C, H) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+                  RAJNI_EINVAL, "rajni_score_select_split: workspace too small (%zu B) or not 16-byte aligned", workspace_bytes);
+    float* ws = static_cast<float*>(workspace);
+    auto s = static_cast<cudaStream_t>(stream);
+    if (int rc = launch_score_stream(static_cast<const __nv_bfloat16*>(qkv), B, N, C, H, ws, s)) return rc;
+    ScoreSelectParams p{};
+    p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+    p.scores_out = scores;
+    p.keep_idx = keep_idx; p.next_scores = next_scores; p.row_map = row_map;
+    p.pre_logit = ws;
+    p.pre_vm = ws + (size_t)B * (((size_t)H * N + 3) & ~(size_t)3);
+    p.N = N; p.C = C; p.H = H; p.keep = keep; p.eps = eps;
+    return launch_score_select(p, B, s);
 }

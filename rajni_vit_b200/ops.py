@@ -97,8 +97,20 @@ def select(scores: torch.Tensor, keep: int, keep_idx=None, next_scores=None, row
     return keep_idx, next_scores, row_map
 
 
+SPLIT_SCORE_MAX_BATCH = 96      # below this many images per launch the K/V pass is spread over (image, row-block) CTAs
+_score_ws = {}
+
+
+def _score_workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    ws = _score_ws.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        _score_ws[dev] = ws
+    return ws
+
+
 def score_select(qkv: torch.Tensor, num_heads: int, keep: int, eps: float = 1e-6, want_scores: bool = False,
-                 keep_idx=None, next_scores=None, row_map=None, scores=None):
+                 keep_idx=None, next_scores=None, row_map=None, scores=None, split: Optional[bool] = None):
     """Fused importance + selection on qkv [B,N,3C] bf16.
     Returns (scores or None, keep_idx, next_scores, row_map)."""
     _bf16c(qkv)
@@ -110,10 +122,19 @@ def score_select(qkv: torch.Tensor, num_heads: int, keep: int, eps: float = 1e-6
     next_scores = torch.empty((B, keep + 1), device=dev, dtype=torch.float32) if next_scores is None else next_scores
     row_map = torch.empty((B * (keep + 1),), device=dev, dtype=torch.int32) if row_map is None else row_map
     C = C3 // 3
+    lib = _lib.load()
+    if split is None:
+        split = B <= SPLIT_SCORE_MAX_BATCH
     # algorithmic bytes: K and V planes + CLS query in, index + carried score out
-    _call("score_select", B * (2 * N * C * 2 + C * 2 + 8 * (keep + 1)), _lib.load().rajni_score_select,
-          qkv.data_ptr(), B, N, C, num_heads, keep, eps, _ptr(scores),
-          keep_idx.data_ptr(), next_scores.data_ptr(), row_map.data_ptr(), _stream(qkv))
+    work = B * (2 * N * C * 2 + C * 2 + 8 * (keep + 1))
+    if split:
+        nbytes = int(lib.rajni_score_select_workspace_bytes(B, N, C, num_heads))
+        ws = _score_workspace(dev, nbytes)
+        _call("score_select", work, lib.rajni_score_select_split, qkv.data_ptr(), B, N, C, num_heads, keep, eps, _ptr(scores),
+              keep_idx.data_ptr(), next_scores.data_ptr(), row_map.data_ptr(), ws.data_ptr(), ws.numel(), _stream(qkv))
+    else:
+        _call("score_select", work, lib.rajni_score_select, qkv.data_ptr(), B, N, C, num_heads, keep, eps, _ptr(scores),
+              keep_idx.data_ptr(), next_scores.data_ptr(), row_map.data_ptr(), _stream(qkv))
     return scores, keep_idx, next_scores, row_map
 
 

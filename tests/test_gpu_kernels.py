@@ -339,3 +339,13 @@ def test_reverse_traversal_hints_do_not_change_results(ops):
         o0 = ops.attention(qkv, None, B, Nt, Nt, H * 64, H, 0.125)
         o1 = ops.attention(qkv, None, B, Nt, Nt, H * 64, H, 0.125, reverse=True)
         assert torch.equal(o0, o1)
+
+
+@pytest.mark.parametrize("B,N,H,ratio", [(8, 197, 12, 0.88), (3, 577, 12, 0.88), (5, 197, 6, 0.7), (4, 197, 16, 0.9)])
+def test_score_select_split_path_is_bit_identical(ops, B, N, H, ratio):
+    """The two-launch path for small batches (rajni_score_select_split) must reproduce the fused kernel exactly."""
+    qkv = dev(make_qkv(B, N, H, 64, 900 + N + H), torch.bfloat16)
+    keep = orc.keep_count(N, ratio)
+    s0, i0, n0, r0 = ops.score_select(qkv, H, keep, want_scores=True, split=False)
+    s1, i1, n1, r1 = ops.score_select(qkv, H, keep, want_scores=True, split=True)
+    assert torch.equal(s0, s1) and torch.equal(i0, i1) and torch.equal(n0, n1) and torch.equal(r0, r1)
