@@ -596,20 +596,21 @@ static int launch_gemm(const void* A, const void* W, GemmParams& p, cudaStream_t
 // (e.g. N = 768, M = 44288: 173 x 3 tiles of 256 = 7.01 waves -> 8, but 173 x 4 tiles of 192 = 9.35 -> 10 x 3/4 = 7.5).
 static int pick_bn(int N, int M, bool exact) {
     if (exact) {
-        static const char* force = getenv("RAJNI_GEMM_BN");                 // debugging aid: force 256 or 192 where it divides N
-        if (force && M > BM && N % atoi(force) == 0 && (atoi(force) == 256 || atoi(force) == 192)) return atoi(force);
+        static const char* force = getenv("RAJNI_GEMM_BN");                 // debugging aid: force a pair-tile width that divides N
+        if (force && M > BM && N % atoi(force) == 0 && (atoi(force) == 256 || atoi(force) == 192 || atoi(force) == 128)) return -atoi(force);
         const bool pair = M > BM;
         int best = 0;
         double best_cost = 0;
-        for (int bn : {256, 192}) {
+        for (int bn : {256, 192, 128}) {
             if (!pair || N % bn) continue;
             const long long tiles = (long long)((M + 2 * BM - 1) / (2 * BM)) * (N / bn);
             const int pairs = num_sms() / 2;
             // the 192-wide tile re-reads A once more per row block: it has to save 8 % of the wave time to be chosen
-            const double cost = (double)((tiles + pairs - 1) / pairs) * bn * (bn == 192 ? 1.08 : 1.0);
+            // (the 128-wide pair tile re-reads A twice as often and halves the work per accumulator hand-over: 20 %)
+            const double cost = (double)((tiles + pairs - 1) / pairs) * bn * (bn == 192 ? 1.08 : bn == 128 ? 1.2 : 1.0);
             if (!best || cost < best_cost) { best = bn; best_cost = cost; }
         }
-        if (best) return best;
+        if (best) return -best;                     // negative: CTA-pair tile
         return N % 256 == 0 ? 256 : N % 128 == 0 ? 128 : 64;
     }
     auto cost = [&](int bn) { long long padded = (long long)((N + bn - 1) / bn) * bn; return bn == 64 ? padded * 3 / 2 : padded; };
@@ -660,13 +661,16 @@ extern "C" int rajni_gemm_bf16_ex(const rajni_gemm_args* a, void* stream) {
     p.row_stats_ld = a->row_stats_ld;
     const bool exact = (flags & (RAJNI_EPI_LN_FOLD | RAJNI_EPI_ROW_STATS)) != 0;
     RAJNI_REQUIRE(!exact || N % 64 == 0, RAJNI_EINVAL, "rajni_gemm_bf16: LN_FOLD / ROW_STATS need N %% 64 == 0 (N=%d)", N);
-    const int bn = pick_bn(N, M, exact);
+    int bn = pick_bn(N, M, exact);                  // < 0: exact CTA-pair tile of width -bn
     auto s = static_cast<cudaStream_t>(stream);
     // wide problems run as CTA pairs (256 x 256 tiles); narrow ones keep single-CTA tiles
     static const bool force_cg1 = getenv("RAJNI_GEMM_CG1") != nullptr;     // debugging aid
+    if (bn < 0 && force_cg1) bn = (-bn == 192) ? 64 : -bn;
     switch (bn) {
+        case -256: return launch_gemm<256, 2>(a->A, a->W, p, s);
+        case -192: return launch_gemm<192, 2>(a->A, a->W, p, s);
+        case -128: return launch_gemm<128, 2>(a->A, a->W, p, s);
         case 256: return (M > BM && !force_cg1) ? launch_gemm<256, 2>(a->A, a->W, p, s) : launch_gemm<256, 1>(a->A, a->W, p, s);
-        case 192: return launch_gemm<192, 2>(a->A, a->W, p, s);
         case 128: return launch_gemm<128, 1>(a->A, a->W, p, s);
         default: return launch_gemm<64, 1>(a->A, a->W, p, s);
     }
