@@ -11,11 +11,11 @@
 //            O += P_j V_j   (TS MMA: A = P_j from TMEM, B = V_j MN-major from shared memory)
 // Recomputing S (4 k-steps) is cheaper than rescaling O in TMEM whenever the maximum moves, and it keeps the softmax
 // exactly two-pass like the reference (no online rescale).
-// Roles (416 threads):
+// Roles (384 threads):
 //   warps 0-7  : softmax + epilogue; each warp owns a 16-row window of the tile through the 16-lane tcgen05.ld/st
 //                shapes (register layout = mma accumulator fragment, verified in tools/probes/tmem16_probe.cu)
 //   warp 8     : tcgen05.mma issuer (one lane); S_{j+1} is issued before P_j V_j so it overlaps the softmax of block j
-//   warps 9-12 : loaders: cp.async row gather of the head's 128-byte Q/K/V slices into 128-byte-swizzled shared memory
+//   warps 9-11 : loaders: cp.async row gather of the head's 128-byte Q/K/V slices into 128-byte-swizzled shared memory
 // TMEM (512 columns): S buffers at [0,224) and [224,448), O at [448,512).
 #include <cuda.h>
 
@@ -26,8 +26,8 @@ namespace rajni {
 constexpr int kAlSoftmaxWarps = 8;
 constexpr int kAlMmaWarp = 8;
 constexpr int kAlLoaderWarp0 = 9;
-constexpr int kAlLoaderThreads = 128;
-constexpr int kAlThreads = (kAlSoftmaxWarps + 1) * 32 + kAlLoaderThreads;    // 416
+constexpr int kAlLoaderThreads = 96;               // 3 warps: 12 warps in all = 3 per scheduler, 168 registers per thread
+constexpr int kAlThreads = (kAlSoftmaxWarps + 1) * 32 + kAlLoaderThreads;    // 384
 constexpr int kAlKB = 224;                         // keys per block
 constexpr int kAlStages = 3;
 constexpr int kAlPlane = kAlKB * 128;              // bytes of one K (or V) block
@@ -151,7 +151,7 @@ attention_long_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         // ================= gather loaders =================
         // A cp.async.mbarrier.arrive holds its thread until the copies have landed (~3000 cycles per block measured), so
         // the loader warps move WHOLE load steps concurrently: warp s (s < 3) owns ring stage s and loads every block
-        // that goes there (one warp per stage keeps the 1-bit barrier parity unambiguous), warp 3 loads the Q tiles.
+        // that goes there (one warp per stage keeps the 1-bit barrier parity unambiguous); warp 0 also loads the Q tiles.
         // Inside a warp 8 lanes move one token's 128-byte head slice, 4 tokens per sweep.
         const int lw = warp - kAlLoaderWarp0;
         const int grp = lane >> 3, chunk = lane & 7;
@@ -167,7 +167,7 @@ attention_long_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 return p.row_map ? (long long)__ldg(p.row_map + (long long)b * Np + j) : (long long)b * p.N_src + j;
             };
             // ---- Q tile of item n into Q buffer n & 1 (rows past Np are zero-filled: finite scores, never stored)
-            if (lw == 3) {
+            if (lw == 0) {
                 const int qb = n & 1;
                 mbar_wait(&q_empty[qb], ((n >> 1) & 1) ^ 1);
                 if (lane == 0) AL_TRACE(n, 0);
@@ -372,42 +372,49 @@ attention_long_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                         p0 = float2_to_bf16x2(e00, e01);
                         p1 = float2_to_bf16x2(e10, e11);
                     };
-                    // The P of S columns [c0, c0+32) lands on columns [c0/2, c0/2+16) of the same 16 lanes: behind what this
-                    // warp still has to read, and no other warp touches these lanes.
-                    auto exp32 = [&](const uint32_t (&cur)[16], int c0) {
-                        uint32_t pk[8];
-                        if (c0 + 32 <= ncol) {
+                    // The P of S columns [c0, c0+64) lands on columns [c0/2, c0/2+32) of the same 16 lanes: behind what this
+                    // warp still has to read, and no other warp touches these lanes.  64-column loads: a tcgen05.ld costs
+                    // 150-330 cycles whatever its size; 32 exp2 per thread hide it.
+                    auto exp64 = [&](const uint32_t (&cur)[32], int c0) {
 #pragma unroll
-                            for (int g = 0; g < 4; ++g)
-                                exp_group(cur[4 * g], cur[4 * g + 1], cur[4 * g + 2], cur[4 * g + 3], 0, false, pk[2 * g], pk[2 * g + 1]);
-                        } else {
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint32_t pk[8];
+                            const int cb = c0 + 32 * hh;
+                            if (cb + 32 <= ncol) {
 #pragma unroll
-                            for (int g = 0; g < 4; ++g)
-                                exp_group(cur[4 * g], cur[4 * g + 1], cur[4 * g + 2], cur[4 * g + 3], c0 + 8 * g + k2, true, pk[2 * g], pk[2 * g + 1]);
+                                for (int g = 0; g < 4; ++g)
+                                    exp_group(cur[16 * hh + 4 * g], cur[16 * hh + 4 * g + 1], cur[16 * hh + 4 * g + 2], cur[16 * hh + 4 * g + 3],
+                                              0, false, pk[2 * g], pk[2 * g + 1]);
+                            } else {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g)
+                                    exp_group(cur[16 * hh + 4 * g], cur[16 * hh + 4 * g + 1], cur[16 * hh + 4 * g + 2], cur[16 * hh + 4 * g + 3],
+                                              cb + 8 * g + k2, true, pk[2 * g], pk[2 * g + 1]);
+                            }
+                            tmem_st16x128_x4(ts + (cb >> 1), pk);
                         }
-                        tmem_st16x128_x4(ts + (c0 >> 1), pk);
                     };
-                    uint32_t xa[16], xb[16];
-                    const int full_end = ncol_pad & ~31;                          // columns covered by whole 32-column chunks
-                    if (full_end > 0) tmem_ld16x256_x4(ts, xa);
-                    for (int c0 = 0; c0 < full_end; c0 += 64) {
+                    uint32_t xa[32], xb[32];
+                    const int full_end = ncol_pad & ~63;                          // columns covered by whole 64-column chunks
+                    if (full_end > 0) tmem_ld16x256_x8(ts, xa);
+                    for (int c0 = 0; c0 < full_end; c0 += 128) {
                         tmem_ld_wait();
-                        if (c0 + 32 < full_end) tmem_ld16x256_x4(ts + c0 + 32, xb);
-                        exp32(xa, c0);
-                        if (c0 + 32 < full_end) {
+                        if (c0 + 64 < full_end) tmem_ld16x256_x8(ts + c0 + 64, xb);
+                        exp64(xa, c0);
+                        if (c0 + 64 < full_end) {
                             tmem_ld_wait();
-                            if (c0 + 64 < full_end) tmem_ld16x256_x4(ts + c0 + 64, xa);
-                            exp32(xb, c0 + 32);
+                            if (c0 + 128 < full_end) tmem_ld16x256_x8(ts + c0 + 128, xa);
+                            exp64(xb, c0 + 64);
                         }
                     }
-                    if (full_end < ncol_pad) {                                    // 16-column tail piece
+                    for (int c0 = full_end; c0 < ncol_pad; c0 += 16) {            // up to three 16-column tail pieces
                         uint32_t vt[8], pk[4];
-                        tmem_ld16x256_x2(ts + full_end, vt);
+                        tmem_ld16x256_x2(ts + c0, vt);
                         tmem_ld_wait();
 #pragma unroll
                         for (int g = 0; g < 2; ++g)
-                            exp_group(vt[4 * g], vt[4 * g + 1], vt[4 * g + 2], vt[4 * g + 3], full_end + 8 * g + k2, true, pk[2 * g], pk[2 * g + 1]);
-                        tmem_st16x128_x2(ts + (full_end >> 1), pk);
+                            exp_group(vt[4 * g], vt[4 * g + 1], vt[4 * g + 2], vt[4 * g + 3], c0 + 8 * g + k2, true, pk[2 * g], pk[2 * g + 1]);
+                        tmem_st16x128_x2(ts + (c0 >> 1), pk);
                     }
                     tmem_st_wait();
                 }
