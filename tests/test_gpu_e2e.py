@@ -264,3 +264,31 @@ def test_cuda_graph_mode_matches_eager(pkg):
     y = model(small)
     model.use_cuda_graph = False
     assert torch.equal(y, model(small))
+
+
+def test_keep_ratio_one_is_identity_and_tiny_ratio_keeps_one_patch(pkg):
+    """attention.py:31-39 edge cases: keep_ratio = 1.0 keeps every token (the block still scores and gathers, the result
+    must equal the un-pruned model bit for bit); a tiny ratio keeps CLS + exactly one patch (keep = max(1, ...))."""
+    x = make_images(3, 224, 21).cuda()
+    dense = build(pkg, "vit_tiny_patch16_224", {})(x)
+    ident = build(pkg, "vit_tiny_patch16_224", {2: {"keep_ratio": 1.0}, 5: {"keep_ratio": 1.0, "update": False}})
+    y = ident(x)
+    assert ident.get_last_stats()["token_counts"] == [197] * 12
+    assert torch.equal(y, dense)
+    for k in ident._last_keep_idx:
+        if k is not None:
+            assert torch.equal(k.cpu().long(), torch.arange(197).expand(3, -1))
+    one = build(pkg, "vit_tiny_patch16_224", {4: {"keep_ratio": 0.001}})
+    y1 = one(x)
+    assert one.get_last_stats()["token_counts"] == [197] * 5 + [2] * 7 and torch.isfinite(y1).all()
+    params = orc.extract_params(copy.deepcopy(one.m).cpu().float())
+    ref, _ = orc.forward(params, x.cpu(), {4: {"keep_ratio": 0.001}}, forced_keep=[None if k is None else k.cpu().long() for k in one._last_keep_idx])
+    assert (y1.cpu() - ref).abs().max().item() < 0.08
+
+
+def test_batch_of_one(pkg):
+    model = build(pkg, "vit_tiny_patch16_224", C1_SCHEDULE)
+    x = make_images(5, 224, 33).cuda()
+    full = model(x)
+    for b in (0, 4):
+        assert torch.equal(model(x[b:b + 1].contiguous()), full[b:b + 1])
