@@ -13,6 +13,7 @@ Prints ONE JSON line (rank 0).  Data-parallel: every rank runs the same per-GPU 
             D2H read of its predictions are inside the timed region (copy/compute double-buffered)
   roofline  the dominant kernel class (the tcgen05 GEMM): algorithmic FLOPs / its CUDA-event time
   cpu_baseline  the CPU oracle port of the reference path on this box's host cores (bounded sample)
+  parity    top-1 agreement and max |dlogit| of the GPU path vs that oracle on the same 16 images (the metric's "top-1 agreement vs ref")
 
 --impl reference times that CPU port alone (the reference is pure Python/eager PyTorch; it cannot be
 pip-installed and /root/reference does not travel to the GPU box, so the oracle port stands in).
@@ -128,6 +129,28 @@ def cpu_port(batch, steps, warmup):
         orc.forward(params, images, SCHEDULE)
     dt = time.time() - t0
     return batch * steps / dt, dt / steps
+
+
+def parity_sample(model, dev, batch=16):
+    """The metric's "top-1 agreement vs ref" on the cpu_baseline sample: the same 16 seeded images through the sm_100a path
+    and through the CPU oracle (fp32, same weights).  `teacher_forced`: the oracle is given OUR kept-token indices, so only
+    the arithmetic is compared; `free_running`: the oracle selects for itself (on random-init weights the scores are nearly
+    flat, so selections - and with them the logits - drift)."""
+    from oracle import rajni_oracle as orc
+    from rajni_vit_b200.vit import create_model
+    params = orc.extract_params(create_model(MODEL, seed=0))
+    images = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(1234))
+    ours = model(images.to(dev)).float().cpu()
+    keep = [None if k is None else k.cpu().long() for k in model._last_keep_idx]
+    counts = model.get_last_stats()["token_counts"]
+    forced, stats = orc.forward(params, images, SCHEDULE, forced_keep=keep)
+    free, _ = orc.forward(params, images, SCHEDULE)
+
+    def cmp(ref):
+        return {"top1_agreement": round((ours.argmax(1) == ref.argmax(1)).float().mean().item(), 4),
+                "max_abs_dlogit": round((ours - ref).abs().max().item(), 4)}
+    return {"images": batch, "token_counts_equal": counts == stats["token_counts"], "logit_std": round(forced.std().item(), 3),
+            "teacher_forced": cmp(forced), "free_running": cmp(free)}
 
 
 def run_reference(args):
@@ -302,6 +325,7 @@ def main():
             ips, t_step = cpu_port(16, 2, 1)
             out["cpu_baseline"] = {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": "port",
                                    "sample": f"3 forwards (1 warm-up + 2 timed) of 16 images, oracle port of the reference path, fp32, {cores} threads"}
+            out["parity"] = parity_sample(model, dev)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
