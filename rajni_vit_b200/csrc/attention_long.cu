@@ -498,7 +498,8 @@ int launch_attention_long(const void* qkv, const int32_t* row_map, void* out, in
     const long long items = (long long)p.BH * p.QT;
     RAJNI_REQUIRE(items < (1LL << 31), RAJNI_EINVAL, "attention_long: too many work items");
     p.n_items = (int)items;
-    static bool attr_done = false;
+    static bool attr_done_dev[kMaxDevices] = {};
+    bool& attr_done = attr_done_dev[current_device()];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAlSmem);
         RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "attention_long: smem attribute (%d B): %s", kAlSmem, cudaGetErrorString(e));

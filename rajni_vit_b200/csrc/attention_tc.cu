@@ -481,7 +481,8 @@ int launch_attention_tc(const void* qkv, const int32_t* row_map, void* out, int 
     const int smem = p.stages * 3 * p.plane_bytes + 256 + 1024;
     CUtensorMap tmap;
     if (int rc = make_tmap_bf16_2d_box(&tmap, qkv, (long long)B * N_src, 3LL * C, 3LL * C, 64, p.Np_pad)) return rc;
-    static int attr_smem = 0;
+    static int attr_smem_dev[kMaxDevices] = {};
+    int& attr_smem = attr_smem_dev[current_device()];
     if (smem > attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "attention_tc: smem attribute (%d B): %s", smem, cudaGetErrorString(e));

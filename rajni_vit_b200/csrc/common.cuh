@@ -34,6 +34,8 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 bool pdl_enabled();      // capi.cu: false when RAJNI_NO_PDL is set
+int current_device();    // capi.cu: cudaGetDevice, 0 on error (indexes the per-device one-time flags below)
+constexpr int kMaxDevices = 64;
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

@@ -531,10 +531,10 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long l
 }
 
 static int num_sms() {
-    static int n = 0;
+    static int n_dev[kMaxDevices] = {};
+    const int dev = current_device();
+    int& n = n_dev[dev];
     if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
     }
@@ -550,7 +550,8 @@ static int launch_gemm_mode(const void* A, const void* W, GemmParams& p, cudaStr
     p.tiles_m = (p.M + BM * CG - 1) / (BM * CG);
     p.tiles_n = (p.N + BN - 1) / BN;
     p.k_blocks = (p.K + BK - 1) / BK;
-    static bool attr_done = false;
+    static bool attr_done_dev[kMaxDevices] = {};          // the attribute is per device (one process may drive several GPUs)
+    bool& attr_done = attr_done_dev[current_device()];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG, MODE, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "gemm: smem attribute (%d B): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
