@@ -157,6 +157,9 @@ class RAJNIViTWrapper(nn.Module):
         sequence of a given input shape is captured once into a CUDA graph and replayed: the 68 launches of a step cost
         ~13 us of host time each, which dominates small batches (vit_tiny at batch 8 is launch-bound).  Graph mode assumes
         frozen weights; ``.to()`` / ``.bfloat16()`` / ``load_state_dict`` drop the captured graphs."""
+        if x.device.type == "cuda" and x.device.index is not None and x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(x.device):          # the C ABI launches on the current device
+                return self.forward(x)
         if not self.use_cuda_graph or x.device.type != "cuda" or x.dim() != 4:
             return self._forward_eager(x)
         key = (tuple(x.shape), x.dtype, x.device)

@@ -292,3 +292,14 @@ def test_batch_of_one(pkg):
     full = model(x)
     for b in (0, 4):
         assert torch.equal(model(x[b:b + 1].contiguous()), full[b:b + 1])
+
+
+def test_second_gpu_in_the_same_process(pkg):
+    """One process driving two GPUs: per-device kernel attributes and the device guard in forward()."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    x = make_images(4, 224, 5)
+    y0 = build(pkg, "vit_tiny_patch16_224", C1_SCHEDULE)(x.cuda())
+    m1 = pkg.RAJNIViTWrapper(__import__("rajni_vit_b200.vit", fromlist=["create_model"]).create_model("vit_tiny_patch16_224", seed=0), C1_SCHEDULE).to("cuda:1").eval()
+    y1 = m1(x.to("cuda:1"))
+    assert torch.equal(y0.cpu(), y1.cpu())
