@@ -244,7 +244,7 @@ def main():
     freed = [torch.cuda.Event() for _ in range(2)]
     preds_host = torch.empty((args.steps, B), dtype=torch.int64).pin_memory()
 
-    def e2e_loop(n):
+    def e2e_loop(n, host=host, stage=stage):
         with torch.cuda.stream(copy_stream):
             stage[0].copy_(host[0], non_blocking=True)
             ready[0].record(copy_stream)
@@ -271,6 +271,21 @@ def main():
         dist.barrier()
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(dt.item())
+
+    # the same loop fed with raw uint8 pixels (extension: normalisation inside the patch kernel, a quarter of the H2D bytes)
+    from rajni_vit_b200.run import IMAGENET_MEAN, IMAGENET_STD
+    model.set_input_normalization(IMAGENET_MEAN, IMAGENET_STD)
+    host8 = [torch.randint(0, 256, (B, 3, 224, 224), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    stage8 = [torch.empty((B, 3, 224, 224), device=dev, dtype=torch.uint8) for _ in range(2)]
+    e2e_loop(2, host8, stage8)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(args.steps, host8, stage8)
+    dt8 = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(dt8, op=dist.ReduceOp.MAX)
+    e2e_u8_value = world * B * args.steps / float(dt8.item())
 
     # ---------------- per-kernel CUDA-event profile (separate instrumented steps) ----------------
     prof = ops.profile_steps(lambda: model(resident[0]), steps=5)
@@ -318,6 +333,8 @@ def main():
             "model_frac_of_tensor_peak": round(value * flops_img / 1e12 / world / peak_tf, 4),
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 4,
                     "d2h_bytes_per_step": B * 8, "note": "pinned fp32 images, H2D double-buffered on a copy stream"},
+            "e2e_uint8": {"value": round(e2e_u8_value, 1), "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224,
+                          "d2h_bytes_per_step": B * 8, "note": "extension: pinned uint8 pixels, ToTensor+Normalize inside the patch kernel"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RAJNI_ABI_VERSION 5
+#define RAJNI_ABI_VERSION 6
 
 enum {
     RAJNI_OK = 0,
@@ -138,15 +138,19 @@ int rajni_attention_fwd(const void* qkv, const int32_t* row_map, void* out,
                         int B, int N_src, int Np, int C, int H, float scale, int reverse, void* stream);
 
 /* ---- a8: patch-embed front end (model.py:31-37)
- * im2col: images [B,3,S,S] (fp32 if images_f32 else bf16) -> cols [B*P, 3*p*p] bf16
- * in Conv2d weight order (c, ky, kx). Also writes the CLS rows
+ * im2col: images [B,3,S,S] (image_dtype: RAJNI_IMG_BF16 / _F32 / _U8) -> cols [B*P, 3*p*p] bf16
+ * in Conv2d weight order (c, ky, kx).  RAJNI_IMG_U8: raw pixels, normalised here as the reference's
+ * loader does in fp32 (run.py:62-70: ToTensor + Normalize): (u/255 - norm[c]) / norm[3+c] with
+ * norm = HOST array {mean[3], std[3]} (read at call time); other dtypes ignore norm (may be NULL).
+ * Also writes the CLS rows
  * x[b,0,:] = cls_pos0[:] (= cls_token + pos_embed[0], precomputed) into x [B,1+P,C] and, when
  * row_stats != NULL, the LayerNorm partials of those rows (slot 0 = (cls_sum, cls_sumsq), the
  * other `stats_slots-1` slots zero) in the layout RAJNI_EPI_ROW_STATS uses. */
-int rajni_patch_im2col(const void* images, int images_f32, int B, int S, int patch,
+enum { RAJNI_IMG_BF16 = 0, RAJNI_IMG_F32 = 1, RAJNI_IMG_U8 = 2 };
+int rajni_patch_im2col(const void* images, int image_dtype, int B, int S, int patch,
                        void* cols, const void* cls_pos0, void* x, int C,
                        float* row_stats, long long row_stats_ld, int stats_slots,
-                       float cls_sum, float cls_sumsq, void* stream);
+                       float cls_sum, float cls_sumsq, const float* norm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "librajni_b200.so")
 
 RAJNI_OK, RAJNI_EINVAL, RAJNI_ECUDA, RAJNI_EARCH, RAJNI_ERANGE = 0, -1, -2, -3, -4
 EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32, EPI_LN_FOLD, EPI_ROW_STATS, HINT_REVERSE_M = 1, 2, 4, 8, 16, 32, 64
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class GemmArgs(Structure):
@@ -50,7 +50,7 @@ SIGNATURES = {
     "rajni_gemm_row_stats_slots": (c_int, [c_int]),
     "rajni_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "rajni_patch_im2col": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
-                                   c_void_p, c_longlong, c_int, c_float, c_float, c_void_p]),
+                                   c_void_p, c_longlong, c_int, c_float, c_float, c_void_p, c_void_p]),
 }
 
 _lib = None

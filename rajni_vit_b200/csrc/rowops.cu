@@ -99,8 +99,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 // One thread moves one (patch, channel, ky) strip: 16 pixels in, 16 bf16 out (two 16-byte
 // stores = one full 32-byte sector).  px is the fastest thread index, so a warp reads
 // contiguous image rows.  Column order (c, ky, kx) matches Conv2d weight.view(C, -1).
-template <bool F32>
-__global__ void __launch_bounds__(256) im2col16_kernel(const void* __restrict__ images, int B, int S,
+// DT: 0 = bf16, 1 = fp32, 2 = uint8 pixels normalised here exactly as torchvision's ToTensor + Normalize do in fp32
+// ((u / 255 - mean[c]) / std[c], IEEE divisions; run.py:62-70), so the bf16 result equals that of the fp32 pipeline.
+struct ImageNorm { float mean[3], std[3]; };
+template <int DT>
+__global__ void __launch_bounds__(256) im2col16_kernel(const void* __restrict__ images, const ImageNorm norm, int B, int S,
                                                        __nv_bfloat16* __restrict__ cols,
                                                        const uint4* __restrict__ cls_pos0,
                                                        uint4* __restrict__ x, int C,
@@ -120,7 +123,23 @@ __global__ void __launch_bounds__(256) im2col16_kernel(const void* __restrict__ 
         int b = (int)(t / G);
         const long long pix = (((long long)b * 3 + c) * S + (py * 16 + ky)) * S + px * 16;
         uint4 o0, o1;
-        if (F32) {
+        if (DT == 2) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(images) + pix));
+            const float mean = norm.mean[c], sd = norm.std[c];
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+            uint32_t o[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float f[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    f[j] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)((w[k] >> (8 * j)) & 0xffu), 255.0f), mean), sd);
+                o[2 * k] = float2_to_bf16x2(f[0], f[1]);
+                o[2 * k + 1] = float2_to_bf16x2(f[2], f[3]);
+            }
+            o0 = make_uint4(o[0], o[1], o[2], o[3]);
+            o1 = make_uint4(o[4], o[5], o[6], o[7]);
+        } else if (DT == 1) {
             const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(images) + pix);
             float4 a = __ldg(src), bb = __ldg(src + 1), cc = __ldg(src + 2), d = __ldg(src + 3);
             o0 = make_uint4(float2_to_bf16x2(a.x, a.y), float2_to_bf16x2(a.z, a.w),
@@ -197,11 +216,20 @@ extern "C" int rajni_layernorm(const void* x, long long in_row_stride, const flo
     return check_launch("layernorm");
 }
 
-extern "C" int rajni_patch_im2col(const void* images, int images_f32, int B, int S, int patch,
+extern "C" int rajni_patch_im2col(const void* images, int image_dtype, int B, int S, int patch,
                                   void* cols, const void* cls_pos0, void* x, int C,
                                   float* row_stats, long long row_stats_ld, int stats_slots,
-                                  float cls_sum, float cls_sumsq, void* stream) {
+                                  float cls_sum, float cls_sumsq, const float* norm, void* stream) {
     RAJNI_REQUIRE(images && cols && cls_pos0 && x, RAJNI_EINVAL, "rajni_patch_im2col: null pointer");
+    RAJNI_REQUIRE(image_dtype >= RAJNI_IMG_BF16 && image_dtype <= RAJNI_IMG_U8, RAJNI_EINVAL, "rajni_patch_im2col: image_dtype %d", image_dtype);
+    RAJNI_REQUIRE(image_dtype != RAJNI_IMG_U8 || norm != nullptr, RAJNI_EINVAL, "rajni_patch_im2col: uint8 images need norm (mean[3], std[3])");
+    ImageNorm nm{{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
+    if (image_dtype == RAJNI_IMG_U8)
+        for (int i = 0; i < 3; ++i) {
+            nm.mean[i] = norm[i];
+            nm.std[i] = norm[3 + i];
+            RAJNI_REQUIRE(nm.std[i] > 0.f, RAJNI_EINVAL, "rajni_patch_im2col: std[%d] must be positive", i);
+        }
     RAJNI_REQUIRE(patch == 16 && S > 0 && S % 16 == 0 && B > 0 && C % 8 == 0, RAJNI_EINVAL,
                   "rajni_patch_im2col: patch=%d S=%d B=%d C=%d unsupported (patch must be 16)", patch, S, B, C);
     RAJNI_REQUIRE(row_stats == nullptr || (stats_slots > 0 && row_stats_ld >= (long long)B * ((S / 16) * (S / 16) + 1)), RAJNI_EINVAL,
@@ -211,8 +239,9 @@ extern "C" int rajni_patch_im2col(const void* images, int images_f32, int B, int
     long long blocks = (strips + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     auto s = static_cast<cudaStream_t>(stream);
-    cudaError_t le = launch_kernel(images_f32 ? im2col16_kernel<true> : im2col16_kernel<false>, dim3((int)blocks), dim3(256), 0, s, 1,
-                                   images, B, S, static_cast<__nv_bfloat16*>(cols), static_cast<const uint4*>(cls_pos0),
+    auto kern = image_dtype == RAJNI_IMG_U8 ? im2col16_kernel<2> : image_dtype == RAJNI_IMG_F32 ? im2col16_kernel<1> : im2col16_kernel<0>;
+    cudaError_t le = launch_kernel(kern, dim3((int)blocks), dim3(256), 0, s, 1,
+                                   images, nm, B, S, static_cast<__nv_bfloat16*>(cols), static_cast<const uint4*>(cls_pos0),
                                    static_cast<uint4*>(x), C, reinterpret_cast<float2*>(row_stats), row_stats_ld, stats_slots,
                                    cls_sum, cls_sumsq);
     count_launch();

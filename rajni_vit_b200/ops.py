@@ -3,6 +3,7 @@ librajni_b200.so does the work.  Every function requires CUDA tensors on an sm_1
 device and raises otherwise (no CPU path)."""
 from __future__ import annotations
 
+import ctypes
 from typing import Optional, Tuple
 
 import torch
@@ -216,17 +217,26 @@ def attention(qkv: torch.Tensor, row_map: Optional[torch.Tensor], B: int, N_src:
     return out
 
 
+_IMG_DTYPES = {torch.bfloat16: 0, torch.float32: 1, torch.uint8: 2}      # RAJNI_IMG_* (include/rajni_b200.h)
+
+
 def patch_im2col(images: torch.Tensor, patch: int, cols: torch.Tensor, cls_pos0: torch.Tensor,
                  x: torch.Tensor, C: int, row_stats: Optional[torch.Tensor] = None, stats_slots: int = 0,
-                 cls_sum: float = 0.0, cls_sumsq: float = 0.0) -> None:
-    """images [B,3,S,S] fp32|bf16 -> cols [B*P, 3*p*p] bf16; also writes the CLS rows of x (and their
-    LayerNorm partial sums into row_stats fp32 [slots, rows, 2])."""
-    if images.dtype not in (torch.float32, torch.bfloat16) or not images.is_contiguous():
-        raise ValueError("images must be contiguous fp32 or bf16")
+                 cls_sum: float = 0.0, cls_sumsq: float = 0.0, norm: Optional[tuple] = None) -> None:
+    """images [B,3,S,S] fp32|bf16|uint8 -> cols [B*P, 3*p*p] bf16; also writes the CLS rows of x (and their
+    LayerNorm partial sums into row_stats fp32 [slots, rows, 2]).  uint8 pixels are normalised in the kernel with
+    ``norm = (mean[3], std[3])`` exactly as ToTensor + Normalize do in fp32 (run.py:62-70)."""
+    if images.dtype not in _IMG_DTYPES or not images.is_contiguous():
+        raise ValueError("images must be contiguous fp32, bf16 or uint8")
+    norm_arr = None
+    if images.dtype == torch.uint8:
+        if norm is None or len(norm[0]) != 3 or len(norm[1]) != 3:
+            raise ValueError("uint8 images need norm=(mean[3], std[3])")
+        norm_arr = (ctypes.c_float * 6)(*[float(v) for v in norm[0]], *[float(v) for v in norm[1]])
     B, ch, S, S2 = images.shape
     if ch != 3 or S != S2:
         raise ValueError(f"images must be [B,3,S,S], got {tuple(images.shape)}")
     _call("patch_im2col", images.numel() * images.element_size() + images.numel() * 2 + B * C * 2,
-          _lib.load().rajni_patch_im2col, images.data_ptr(), int(images.dtype == torch.float32), B, S, patch,
+          _lib.load().rajni_patch_im2col, images.data_ptr(), _IMG_DTYPES[images.dtype], B, S, patch,
           cols.data_ptr(), cls_pos0.data_ptr(), x.data_ptr(), C, _ptr(row_stats),
-          0 if row_stats is None else row_stats.shape[1], stats_slots, cls_sum, cls_sumsq, _stream(images))
+          0 if row_stats is None else row_stats.shape[1], stats_slots, cls_sum, cls_sumsq, norm_arr, _stream(images))

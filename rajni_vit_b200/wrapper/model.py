@@ -65,7 +65,18 @@ class RAJNIViTWrapper(nn.Module):
         self._ws = {}
         self._graphs = {}
         self.use_cuda_graph = os.environ.get("RAJNI_CUDA_GRAPH", "") not in ("", "0")
+        self.input_norm: Optional[tuple] = None       # (mean[3], std[3]) for uint8 images, see set_input_normalization
         self._validate()
+
+    def set_input_normalization(self, mean, std) -> "RAJNIViTWrapper":
+        """Extension (not in the reference): accept raw uint8 pixels [B,3,S,S] and apply the loader's ToTensor + Normalize
+        (run.py:62-70) inside the patch kernel - a quarter of the host-to-device bytes of fp32 images, same logits."""
+        mean, std = tuple(float(v) for v in mean), tuple(float(v) for v in std)
+        if len(mean) != 3 or len(std) != 3 or min(std) <= 0:
+            raise ValueError("mean and std must have three entries, std positive")
+        self.input_norm = (mean, std)
+        self._graphs = {}
+        return self
 
     # ------------------------------------------------------------------ contract checks
     def _validate(self):
@@ -192,7 +203,10 @@ class RAJNIViTWrapper(nn.Module):
                         raise NotImplementedError("dropout in training mode is not supported (inference path)")
         m = self.m
         out_dtype = x.dtype if x.dtype.is_floating_point else torch.float32
-        if x.dtype not in (torch.float32, torch.bfloat16):
+        if x.dtype == torch.uint8:
+            if self.input_norm is None:
+                raise TypeError("uint8 images need set_input_normalization(mean, std) first (the reference takes normalised floats)")
+        elif x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()
         x = x.contiguous()
         B, _, S, _ = x.shape
@@ -213,7 +227,7 @@ class RAJNIViTWrapper(nn.Module):
         cur, nxt = ws["xa"], ws["xb"]
         stats, slots = ws["stats"], ws["stat_slots"]
         ops.patch_im2col(x, 16, ws["cols"], cls_pos0, cur, C, row_stats=stats, stats_slots=slots,
-                         cls_sum=cls_sum, cls_sumsq=cls_sumsq)
+                         cls_sum=cls_sum, cls_sumsq=cls_sumsq, norm=self.input_norm if x.dtype == torch.uint8 else None)
         ops.gemm(ws["cols"], pe_w, pe_b, B * P, C, 768, residual=pos, ldres=C, res_row_map=ws["embed_pos_map"],
                  out=cur, ldd=C, out_row_map=ws["embed_out_map"], row_stats=stats, tag="embed")
 

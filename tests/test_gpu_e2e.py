@@ -249,6 +249,31 @@ def test_cli_synthetic(pkg, tmp_path, capsys):
     assert res["base"][1] > 0 and res["rajni"][1] > 0
 
 
+def test_uint8_input_matches_float_pipeline(pkg, tmp_path, capsys):
+    """Extension: raw uint8 pixels, ToTensor + Normalize (run.py:62-70) applied inside the patch kernel.  The fp32 loader
+    pipeline (u/255, -mean, /std in IEEE fp32) gives the same bf16 patches, so the logits must be bit-identical."""
+    from rajni_vit_b200 import run
+    model = build(pkg, "vit_tiny_patch16_224", C1_SCHEDULE)
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (8, 3, 224, 224), generator=g, dtype=torch.uint8)
+    u8[0, :, :2] = torch.tensor([0, 255], dtype=torch.uint8)[None, :, None]           # the extremes are in
+    mean, std = torch.tensor(run.IMAGENET_MEAN), torch.tensor(run.IMAGENET_STD)
+    xf = u8.float().div(255).sub(mean[None, :, None, None]).div(std[None, :, None, None])
+    ref = model(xf.cuda()).clone()
+    with pytest.raises(TypeError):
+        model(u8.cuda())                                                              # no normalisation configured
+    model.set_input_normalization(run.IMAGENET_MEAN, run.IMAGENET_STD)
+    got = model(u8.cuda())
+    assert got.dtype == torch.float32 and torch.equal(got, ref)
+    assert torch.equal(model(xf.cuda()), ref)                                         # floats still take the float path
+    # and through the CLI
+    sched = tmp_path / "schedule.json"
+    sched.write_text(json.dumps({"3": {"keep_ratio": 0.9}}))
+    res = run.main(["--synthetic", "2", "--batch_size", "4", "--model", "vit_tiny_patch16_224", "--schedule", str(sched),
+                    "--warmup", "1", "--uint8_input", "--compare_base"])
+    assert res["rajni"][1] > 0 and "token_counts [197, 197, 197, 197, 177" in capsys.readouterr().out
+
+
 def test_cuda_graph_mode_matches_eager(pkg):
     """Opt-in graph replay: bit-identical logits and the same stats as the eager launch sequence, across replays and
     after a shape change."""

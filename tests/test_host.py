@@ -165,7 +165,7 @@ def test_cli_flags_match_reference():
     from rajni_vit_b200 import run
     a = run.get_args(["--data_path", "/x", "--schedule", "s.json", "--compare_base", "--max_batches", "3"])
     assert (a.batch_size, a.num_workers, a.pin_mem, a.model, a.device, a.warmup) == (256, 8, True, "vit_base_patch16_224", "cuda", 5)
-    assert a.compare_base and a.max_batches == 3 and a.schedule == "s.json"
+    assert a.compare_base and a.max_batches == 3 and a.schedule == "s.json" and not a.uint8_input
     with pytest.raises(SystemExit):
         run.get_args(["--schedule", "s.json"])                  # neither --data_path nor --synthetic
 
