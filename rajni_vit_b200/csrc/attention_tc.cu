@@ -15,7 +15,7 @@
 //                     kept-token gather needs no separate pass over HBM
 // Per tile:  S = Q K^T (SS MMA, fp32 in TMEM) -> two passes over the TMEM row (max; exp2/sum) ->
 //            P written back over S as packed bf16 -> O = P V (TS MMA: A from TMEM, V MN-major from smem)
-//            -> O/rowsum -> bf16 -> 32-byte global stores.
+//            -> O/rowsum -> bf16 -> swizzled shared memory -> one TMA store per warp (32 rows x 128 B, clipped at Np).
 // TMEM: 512 columns = 2 tiles x 256: S at [0,Np_pad), P at [0,Np_pad/2), O at [192,256) when Np_pad <= 192
 // (then S of the next unit never waits for the O read-out), else at [128,192).
 // Measured on B200 (tools/probes/mma_probe.cu): a tcgen05.mma with M=128 costs >= 94 cycles whatever N is,
@@ -34,7 +34,8 @@ constexpr int kAtLoaderThreads = 128;
 constexpr int kAtThreads = (kAtSoftmaxWarps + 1) * 32 + kAtLoaderThreads;     // 416
 constexpr int kAtMaxStages = 4;
 constexpr int kAtTileCols = 256;
-constexpr int kAtSmemBudget = 224 * 1024;                                     // stages; barriers and alignment on top
+constexpr int kAtOutStage = kAtSoftmaxWarps * 32 * 128;                        // output staging: 32 rows x 128 B per softmax warp
+constexpr int kAtSmemBudget = 224 * 1024 - kAtOutStage;                        // stages; barriers and alignment on top
 
 // Optional event trace (tools/probes/attn_trace.cu builds this file with -DRAJNI_ATTN_TRACE): clock64 stamps of
 // CTA 0's pipeline events, one row of 32 slots per unit.  Compiles to nothing in the library.
@@ -63,6 +64,9 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, 
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -86,13 +90,14 @@ __device__ __forceinline__ int unit_item(const AttnTcParams& p, int u, int t) {
 }
 
 __global__ void __launch_bounds__(kAtThreads, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, const AttnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const int stage_bytes = 3 * p.plane_bytes;
+    // [stages][Q|K|V planes] [output staging: 8 warps x 4 KB] [barriers]
     // (tile 1's Q operand is read as 128 rows from row 128 of its plane: the over-read lands in the stage's K plane)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + p.stages * stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + p.stages * stage_bytes + kAtOutStage);
     uint64_t* qk_full = bars;                      // [4] loader -> MMA   (TMA transaction bytes of Q and K)
     uint64_t* v_full = bars + kAtMaxStages;        // [4] loader -> MMA   (V)
     uint64_t* empty_bar = bars + 2 * kAtMaxStages; // [4] MMA -> loader   (tcgen05.commit)
@@ -319,6 +324,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPa
             const uint32_t ph = n & 1;
             const int q = (p.two_tiles ? t * 128 : 0) + row;                   // query index inside the image
             const bool warp_live = q - lane < Np;                              // any valid row in this warp
+            const int item_b = item / p.H, item_h = item - item_b * p.H;       // (before the wait for S: off the critical path)
             mbar_wait(&s_full[t], ph);
             tc_fence_after();
             if ((tid & 127) == 0) AT_TRACE(n, 12 + 8 * t);
@@ -394,6 +400,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPa
             if ((tid & 127) == 0) AT_TRACE(n, 14 + 8 * t);
             mbar_arrive(&p_full[t]);
             // ---- O = P V done -> normalise, store
+            if (warp_live) {                  // while P V runs: the previous store must have read the staging buffer
+                if (lane == 0) bulk_wait_group_read<0>();
+                __syncwarp();
+            }
             mbar_wait(&o_full[t], ph);
             tc_fence_after();
             if ((tid & 127) == 0) AT_TRACE(n, 15 + 8 * t);
@@ -405,26 +415,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPa
                 tc_fence_before();
                 mbar_arrive(&o_empty[t]);
                 if ((tid & 127) == 0) AT_TRACE(n, 16 + 8 * t);
-                if (q < Np) {
-                    const float inv = 1.f / sum;
-                    const int b = item / p.H, h = item - b * p.H;
-                    __nv_bfloat16* dst = p.out + ((long long)b * Np + q) * p.C + h * 64;
+                // The warp's 32 rows x 128 B go out as ONE TMA store (3-d map: rows past the image's Np are clipped), staged
+                // in shared memory with the 128-byte swizzle.  (Against 32-byte st.global per row: -3 % kernel time.)
+                const uint32_t s_out = smem_base + p.stages * stage_bytes + warp * 4096;
+                const float inv = 1.f / sum;
+                const uint32_t srow = s_out + lane * 128;
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t w[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            w[i] = float2_to_bf16x2(__uint_as_float(o0[16 * c + 2 * i]) * inv, __uint_as_float(o0[16 * c + 2 * i + 1]) * inv);
-                        st_global_256(dst + 16 * c, w);
-                    }
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t w[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            w[i] = float2_to_bf16x2(__uint_as_float(o1[16 * c + 2 * i]) * inv, __uint_as_float(o1[16 * c + 2 * i + 1]) * inv);
-                        st_global_256(dst + 32 + 16 * c, w);
-                    }
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t (&src)[32] = c < 4 ? o0 : o1;
+                    const int j = (c & 3) * 8;
+                    sts128(srow + ((c ^ (lane & 7)) << 4),
+                           float2_to_bf16x2(__uint_as_float(src[j]) * inv, __uint_as_float(src[j + 1]) * inv),
+                           float2_to_bf16x2(__uint_as_float(src[j + 2]) * inv, __uint_as_float(src[j + 3]) * inv),
+                           float2_to_bf16x2(__uint_as_float(src[j + 4]) * inv, __uint_as_float(src[j + 5]) * inv),
+                           float2_to_bf16x2(__uint_as_float(src[j + 6]) * inv, __uint_as_float(src[j + 7]) * inv));
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_3d(&tmap_out, s_out, item_h * 64, q - lane, item_b);
+                    bulk_commit_group();
                 }
                 if ((tid & 127) == 0) AT_TRACE(n, 17 + 8 * t);
             } else {
@@ -433,6 +443,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPa
             }
         }
     }
+    if (warp < kAtSoftmaxWarps && lane == 0) bulk_wait_group<0>();           // output stores complete before the CTA retires
     tc_fence_before();
     __syncthreads();
     if (warp == kAtMmaWarp) {
@@ -443,6 +454,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPa
 
 int make_tmap_bf16_2d_box(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems,
                           int box_cols, int box_rows);      // gemm_tcgen05.cu
+int make_tmap_bf16_3d_box(CUtensorMap* map, const void* base, long long batch, long long rows, long long cols, int box_rows);
 
 static int at_num_sms() {
     static int n = 0;
@@ -478,9 +490,11 @@ int launch_attention_tc(const void* qkv, const int32_t* row_map, void* out, int 
     p.stages = kAtSmemBudget / (3 * p.plane_bytes);
     if (p.stages > kAtMaxStages) p.stages = kAtMaxStages;
     RAJNI_REQUIRE(p.stages >= 2, RAJNI_EINVAL, "attention_tc: Np=%d leaves room for %d stage(s)", Np, p.stages);
-    const int smem = p.stages * 3 * p.plane_bytes + 256 + 1024;
+    const int smem = p.stages * 3 * p.plane_bytes + kAtOutStage + 256 + 1024;
     CUtensorMap tmap;
     if (int rc = make_tmap_bf16_2d_box(&tmap, qkv, (long long)B * N_src, 3LL * C, 3LL * C, 64, p.Np_pad)) return rc;
+    CUtensorMap tmap_out;
+    if (int rc = make_tmap_bf16_3d_box(&tmap_out, out, B, Np, C, 32)) return rc;
     static int attr_smem_dev[kMaxDevices] = {};
     int& attr_smem = attr_smem_dev[current_device()];
     if (smem > attr_smem) {
@@ -488,8 +502,10 @@ int launch_attention_tc(const void* qkv, const int32_t* row_map, void* out, int 
         RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "attention_tc: smem attribute (%d B): %s", smem, cudaGetErrorString(e));
         attr_smem = smem;
     }
-    const int grid = p.n_units < at_num_sms() ? p.n_units : at_num_sms();
-    cudaError_t le = launch_kernel(attention_tc_kernel, dim3(grid), dim3(kAtThreads), (size_t)smem, stream, 1, tmap, p);
+    int grid = p.n_units < at_num_sms() ? p.n_units : at_num_sms();
+    static const int cta_cap = getenv("RAJNI_ATTN_MAX_CTAS") ? atoi(getenv("RAJNI_ATTN_MAX_CTAS")) : 0;      // experiments: share the GPU
+    if (cta_cap > 0 && grid > cta_cap) grid = cta_cap;
+    cudaError_t le = launch_kernel(attention_tc_kernel, dim3(grid), dim3(kAtThreads), (size_t)smem, stream, 1, tmap, tmap_out, p);
     count_launch();
     RAJNI_REQUIRE(le == cudaSuccess, RAJNI_ECUDA, "attention_tc: launch failed: %s", cudaGetErrorString(le));
     int rc = check_launch("attention_tc");

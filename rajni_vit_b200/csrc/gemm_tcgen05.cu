@@ -525,6 +525,22 @@ int make_tmap_bf16_2d_box(CUtensorMap* map, const void* base, long long rows, lo
                   (int)r, rows, cols, ld_elems, box_rows, box_cols);
     return 0;
 }
+// [batch][rows][cols] bf16 tensor, densely packed, box = box_rows x 64 columns of one batch entry, 128-byte swizzle.
+// (Used for stores that must be clipped at the end of each batch entry's rows.)
+int make_tmap_bf16_3d_box(CUtensorMap* map, const void* base, long long batch, long long rows, long long cols, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    RAJNI_REQUIRE(fn != nullptr, RAJNI_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * (cuuint64_t)cols * 2};
+    cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RAJNI_REQUIRE(r == CUDA_SUCCESS, RAJNI_ECUDA, "cuTensorMapEncodeTiled (3d) failed (%d) batch=%lld rows=%lld cols=%lld",
+                  (int)r, batch, rows, cols);
+    return 0;
+}
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols,
                       long long ld_elems, int box_rows) {
     return make_tmap_bf16_2d_box(map, base, rows, cols, ld_elems, 64, box_rows);
@@ -558,7 +574,9 @@ static int launch_gemm_mode(const void* A, const void* W, GemmParams& p, cudaStr
         attr_done = true;
     }
     int grid = p.tiles_m * p.tiles_n * CG;
-    const int max_grid = (num_sms() / CG) * CG;
+    int max_grid = (num_sms() / CG) * CG;
+    static const int cta_cap = getenv("RAJNI_GEMM_MAX_CTAS") ? atoi(getenv("RAJNI_GEMM_MAX_CTAS")) : 0;     // experiments: leave SMs free
+    if (cta_cap > 0 && cta_cap < max_grid) max_grid = (cta_cap / CG) * CG;
     if (grid > max_grid) grid = max_grid;
     cudaError_t e = launch_kernel(gemm_bf16_kernel<BN, CG, MODE, LN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, CG,
                                   ta, tb, p);

@@ -80,7 +80,7 @@ def main():
             idx = torch.stack([torch.sort(torch.randperm(N, device="cuda")[:Np]).values for _ in range(B)])
             rmap = (idx + torch.arange(B, device="cuda")[:, None] * N).int().flatten()
         out = torch.empty(B * Np, 768, device="cuda", dtype=torch.bfloat16)
-        t = timeit(lambda: ops.attention(qkv, rmap, B, N, Np, 768, 12, 0.125, out=out))
+        t = timeit(lambda: ops.attention(qkv, rmap, B, N, Np, 768, 12, 0.125, out=out), inner=8)
         fl = 4.0 * B * Np * Np * 768
         print(f"attention N={N:3d} Np={Np:3d}        {t*1e6:8.1f} us  {fl/t/1e12:7.1f} TF/s")
     if not want("rows"):

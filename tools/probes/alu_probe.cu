@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(1024) alu_kernel(int reps, long long* out, flo
 #pragma unroll
     for (int i = 0; i < 8; ++i) { x[i] = -(threadIdx.x * 1e-3f + i); y[i] = f2pack(x[i], x[i] + 0.5f); }
     const uint64_t c2 = f2pack(0.999f, 1.001f), d2 = f2pack(-1e-3f, -2e-3f);
+    float acc0 = 0.f;
     __syncthreads();
     long long t0 = clock64();
 #pragma unroll 1
@@ -36,13 +37,24 @@ __global__ void __launch_bounds__(1024) alu_kernel(int reps, long long* out, flo
             else if (WHICH == 1) x[i] = fmaf(x[i], 0.999f, -1e-3f);
             else if (WHICH == 2) y[i] = fma2(y[i], c2, d2);
             else if (WHICH == 3) x[i] = -ex2_poly(x[i]);
-            else { x[i] = -ex2(x[i]); y[i] = fma2(y[i], c2, d2); y[i] = fma2(y[i], c2, d2); }     // 1 MUFU : 2 FFMA2
+            else if (WHICH == 4) { x[i] = -ex2(x[i]); y[i] = fma2(y[i], c2, d2); y[i] = fma2(y[i], c2, d2); }     // 1 MUFU : 2 FFMA2
+            else if (WHICH == 5) x[i] = __uint_as_float(float2_to_bf16x2(x[i], x[(i + 1) & 7]));        // F2FP.BF16 pack alone
+            else if (WHICH == 6 || WHICH == 7 || WHICH == 8) {
+                // the softmax exp pass per element pair: 2 FFMA, 2 MUFU.EX2, 2 FADD, 1 pack
+                const float e0 = ex2(fmaf(x[i], 0.18f, -0.05f)), e1 = ex2(fmaf(x[(i + 1) & 7], 0.18f, -0.05f));
+                acc0 += e0 + e1;
+                uint32_t pk;
+                if (WHICH == 6) pk = float2_to_bf16x2(e0, e1);
+                else if (WHICH == 7) pk = __byte_perm(__float_as_uint(e0) + 0x8000u, __float_as_uint(e1) + 0x8000u, 0x7632);   // round half up, integer pipe
+                else pk = __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632);                                      // truncate
+                x[i] = -__uint_as_float(pk & 0x3fff3fffu);
+            }
         }
     }
     long long t1 = clock64();
     __syncthreads();
     if (threadIdx.x == 0) out[0] = t1 - t0;
-    float acc = 0.f;
+    float acc = acc0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { float a, b; f2unpack(y[i], a, b); acc += x[i] + a + b; }
     sink[threadIdx.x] = acc;
@@ -67,5 +79,9 @@ int main() {
     run<2>("FFMA2 (2 fma each)", o, sk);
     run<3>("exp2 poly (FMA pipe)", o, sk);
     run<4>("MUFU + 2 FFMA2 mix", o, sk);
+    run<5>("F2FP.BF16 pack", o, sk);
+    run<6>("exp pair, cvt pack", o, sk);
+    run<7>("exp pair, int round", o, sk);
+    run<8>("exp pair, truncate", o, sk);
     return 0;
 }

@@ -4,7 +4,7 @@
 #include <cstdlib>
 #include <vector>
 #include "../../rajni_vit_b200/csrc/attention_tc.cu"
-namespace rajni { void set_error(const char*, ...) {} void count_launch(int) {} int check_launch(const char*) { return cudaGetLastError() == cudaSuccess ? 0 : -2; } bool pdl_enabled() { return false; } }
+namespace rajni { void set_error(const char*, ...) {} void count_launch(int) {} int check_launch(const char*) { return cudaGetLastError() == cudaSuccess ? 0 : -2; } bool pdl_enabled() { return false; } int current_device() { return 0; } }
 int main(int argc, char** argv) {
     const int B = 256, H = 12, C = 768;
     const int N = argc > 1 ? atoi(argv[1]) : 197, Np = argc > 2 ? atoi(argv[2]) : 173;
