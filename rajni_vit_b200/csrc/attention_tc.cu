@@ -494,6 +494,7 @@ int launch_attention_tc(const void* qkv, const int32_t* row_map, void* out, int 
     CUtensorMap tmap;
     if (int rc = make_tmap_bf16_2d_box(&tmap, qkv, (long long)B * N_src, 3LL * C, 3LL * C, 64, p.Np_pad)) return rc;
     CUtensorMap tmap_out;
+    RAJNI_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15u) == 0, RAJNI_EINVAL, "attention_tc: out must be 16-byte aligned (TMA store)");
     if (int rc = make_tmap_bf16_3d_box(&tmap_out, out, B, Np, C, 32)) return rc;
     static int attr_smem_dev[kMaxDevices] = {};
     int& attr_smem = attr_smem_dev[current_device()];

@@ -43,6 +43,9 @@ def _is_identity(m) -> bool:
     return m is None or isinstance(m, nn.Identity) or (isinstance(m, nn.Dropout) and m.p == 0.0)
 
 
+AUTO_GRAPH_MAX_ROWS = 16384       # batch x tokens up to which forward() replays a CUDA graph by default
+
+
 class RAJNIViTWrapper(nn.Module):
     def __init__(self, base_model: nn.Module, pruning_schedule: Dict[int, Dict]):
         super().__init__()
@@ -64,7 +67,9 @@ class RAJNIViTWrapper(nn.Module):
         self._packs = PackCache()
         self._ws = {}
         self._graphs = {}
-        self.use_cuda_graph = os.environ.get("RAJNI_CUDA_GRAPH", "") not in ("", "0")
+        # None = automatic: replay a captured CUDA graph when the batch is small enough to be launch-bound
+        env = os.environ.get("RAJNI_CUDA_GRAPH", "")
+        self.use_cuda_graph: Optional[bool] = None if env == "" else env != "0"
         self.input_norm: Optional[tuple] = None       # (mean[3], std[3]) for uint8 images, see set_input_normalization
         self._validate()
 
@@ -159,32 +164,39 @@ class RAJNIViTWrapper(nn.Module):
             sel={},
         )
         self._ws = {key: ws}        # keep one shape resident
+        self._graphs = {}           # a captured graph points into the workspace it was captured with
         return ws
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """model.py:30-69.  With ``use_cuda_graph`` (attribute, or RAJNI_CUDA_GRAPH=1 in the environment) the launch
-        sequence of a given input shape is captured once into a CUDA graph and replayed: the 68 launches of a step cost
-        ~13 us of host time each, which dominates small batches (vit_tiny at batch 8 is launch-bound).  Graph mode assumes
-        frozen weights; ``.to()`` / ``.bfloat16()`` / ``load_state_dict`` drop the captured graphs."""
+        """model.py:30-69.  The launch sequence of a given input shape can be captured once into a CUDA graph and replayed:
+        the 68 launches of a step cost ~13 us of host time each, which dominates small batches (vit_tiny at batch 8:
+        0.88 -> 0.53 ms per step).  ``use_cuda_graph`` = None (default) replays when the batch has at most
+        ``AUTO_GRAPH_MAX_ROWS`` token rows, True / False force it (RAJNI_CUDA_GRAPH=1 / 0 in the environment do the same).
+        A captured graph is dropped when any parameter changes (storage or version), on ``.to()`` / ``.bfloat16()`` /
+        ``load_state_dict`` and when the input normalisation changes; results are bit-identical to the eager sequence."""
         if x.device.type == "cuda" and x.device.index is not None and x.device.index != torch.cuda.current_device():
             with torch.cuda.device(x.device):          # the C ABI launches on the current device
                 return self.forward(x)
-        if not self.use_cuda_graph or x.device.type != "cuda" or x.dim() != 4:
+        use = self.use_cuda_graph
+        if use is None and x.dim() == 4:
+            use = x.shape[0] * ((x.shape[2] // 16) * (x.shape[3] // 16) + 1) <= AUTO_GRAPH_MAX_ROWS
+        if not use or x.device.type != "cuda" or x.dim() != 4 or ops._prof is not None:      # (the per-kernel profiler times eager launches)
             return self._forward_eager(x)
-        key = (tuple(x.shape), x.dtype, x.device)
+        key = (tuple(x.shape), x.dtype, x.device, self.training)
+        wsig = tuple((q.data_ptr(), q._version) for q in self.parameters())
         entry = self._graphs.get(key)
-        if entry is None:
+        if entry is None or entry[5] != wsig:
             x_static = x.clone()
             self._forward_eager(x_static)                       # builds packs and workspace, warms every kernel
             torch.cuda.synchronize(x.device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 y_static = self._forward_eager(x_static)
-            entry = (graph, x_static, y_static, self._last_stats, self._last_keep_idx)
+            entry = (graph, x_static, y_static, self._last_stats, self._last_keep_idx, wsig)
             self._graphs = {key: entry}                         # one shape resident, like the workspace
-        graph, x_static, y_static, stats, keep = entry
+        graph, x_static, y_static, stats, keep, _ = entry
         x_static.copy_(x)
         graph.replay()
         self._last_stats, self._last_keep_idx = stats, keep

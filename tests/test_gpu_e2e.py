@@ -279,6 +279,8 @@ def test_cuda_graph_mode_matches_eager(pkg):
     after a shape change."""
     model = build(pkg, "vit_tiny_patch16_224", C1_SCHEDULE)
     x1, x2 = make_images(8, 224, 7).cuda(), make_images(8, 224, 8).cuda()
+    assert model.use_cuda_graph is None                          # default: automatic (small batches replay a graph)
+    model.use_cuda_graph = False
     ref1, ref2 = model(x1).clone(), model(x2).clone()
     stats = model.get_last_stats()
     model.use_cuda_graph = True
@@ -289,6 +291,17 @@ def test_cuda_graph_mode_matches_eager(pkg):
     y = model(small)
     model.use_cuda_graph = False
     assert torch.equal(y, model(small))
+    # automatic mode: graph at batch 8, eager at a batch too large for it (which replaces the workspace the graph was
+    # captured with), graph again; and an in-place weight update must not be served from a stale graph
+    model.use_cuda_graph = None
+    big = make_images(96, 224, 10).cuda()                       # 96 * 197 rows > AUTO_GRAPH_MAX_ROWS
+    assert torch.equal(model(x1), ref1) and len(model._graphs) == 1
+    yb = model(big)
+    assert len(model._graphs) == 0 and torch.equal(yb[:8], model(big[:8].contiguous()))
+    assert torch.equal(model(x1), ref1) and torch.equal(model(x1), ref1)
+    with torch.no_grad():
+        model.m.head.bias.add_(1.0)
+    assert torch.allclose(model(x1), ref1 + 1.0, atol=1e-5)
 
 
 def test_keep_ratio_one_is_identity_and_tiny_ratio_keeps_one_patch(pkg):

@@ -21,7 +21,7 @@ for name, model_name, sched, B, S in CASES:
     if only and not any(o in name for o in only):
         continue
     m = RAJNIViTWrapper(create_model(model_name, seed=0), sched).cuda().eval()
-    m.use_cuda_graph = os.environ.get("RAJNI_CUDA_GRAPH", "") not in ("", "0")
+    m.use_cuda_graph = {"": None, "0": False}.get(os.environ.get("RAJNI_CUDA_GRAPH", ""), True)     # default: automatic
     x = torch.randn(B, 3, S, S, device="cuda")
     for _ in range(5):
         m(x)
