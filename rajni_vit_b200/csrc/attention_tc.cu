@@ -52,6 +52,7 @@ struct AttnTcParams {
     __nv_bfloat16* out;
     int N_src, Np, Np_pad, C, H, BH, two_tiles, n_units;
     int o_col, o_outside;       // TMEM column of O inside a tile; o_outside = O does not overlap S's columns
+    int split_col;              // > 0 (needs o_outside): P V starts once P's columns [0, split_col) are written, the rest follows
     int plane_bytes, stages;    // bytes of one Q/K/V plane of a stage (1024-aligned); pipeline depth
     int reverse;                // walk the (image, head) items last-to-first (L2 reuse hint)
     float scale_log2;
@@ -105,7 +106,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     uint64_t* p_full = s_full + 2;                 // [2 tiles] softmax -> MMA (P in TMEM, 128 arrivals)
     uint64_t* o_full = s_full + 4;                 // [2 tiles] MMA -> softmax (O ready)
     uint64_t* o_empty = s_full + 6;                // [2 tiles] softmax -> MMA (O read out)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
+    uint64_t* p_half = s_full + 8;                 // [2 tiles] softmax -> MMA (first split_col columns of P in TMEM)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 10);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -121,6 +123,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&s_full[i], 1);
                 mbar_init(&p_full[i], 128);
+                mbar_init(&p_half[i], 128);
                 mbar_init(&o_full[i], 1);
                 mbar_init(&o_empty[i], 128);
             }
@@ -245,12 +248,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             uint32_t s_phase[2] = {0, 0}, pv_phase[2] = {0, 0};
             uint32_t pv_cnt = 0;                                              // PVs issued per stage, 4 bits each
             int qk_seen = 0, v_seen = 0;                                      // units whose Q/K (V) have been seen landed
+            bool half_done[2] = {false, false};                               // the first part of the current P V is queued
             while (pv_next[0] < cnt[0] || pv_next[1] < cnt[1]) {
                 bool did = false;
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     const uint32_t tt = tmem_base + t * kAtTileCols;
                     int n = pv_next[t];
+                    if (p.split_col && !half_done[t] && n < cnt[t] && s_next[t] > n && mbar_test(&p_half[t], n & 1) &&
+                        (n == 0 || mbar_test(&o_empty[t], (n - 1) & 1))) {
+                        // the first columns of P(n, t) are in TMEM: start P V under the rest of the exp pass
+                        const int st = pv_stage[t];
+                        bool ok = true;
+                        if (v_seen <= n) {
+                            if (mbar_test(&v_full[st], pv_phase[t])) v_seen = n + 1;
+                            else ok = false;
+                        }
+                        if (ok) {
+                            tc_fence_after();
+                            AT_TRACE(n, 4 + 4 * t);
+                            const uint64_t vd = vd0 + (uint64_t)((st * stage_bytes + t * kv_stride) >> 4);
+                            for (int k = 0; k < p.split_col / 16; ++k)
+                                umma_bf16_ts(tt + p.o_col, tt + k * 8, vd + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0);
+                            half_done[t] = true;
+                            did = true;
+                        }
+                    }
                     if (n < cnt[t] && s_next[t] > n && mbar_test(&p_full[t], n & 1) &&
                         (n == 0 || !p.o_outside || mbar_test(&o_empty[t], (n - 1) & 1))) {
                         // P(n, t) is in TMEM and O(n-1, t) has been read out
@@ -262,10 +285,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
                         }
                         if (ok) {
                             tc_fence_after();
-                            AT_TRACE(n, 4 + 4 * t);
+                            if (!half_done[t]) AT_TRACE(n, 4 + 4 * t);
                             const uint64_t vd = vd0 + (uint64_t)((st * stage_bytes + t * kv_stride) >> 4);
-                            for (int k = 0; k < nk; ++k)
+                            for (int k = half_done[t] ? p.split_col / 16 : 0; k < nk; ++k)
                                 umma_bf16_ts(tt + p.o_col, tt + k * 8, vd + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0);
+                            half_done[t] = false;
                             umma_commit(&o_full[t]);
                             AT_TRACE(n, 5 + 4 * t);
                             pv_next[t] = n + 1;
@@ -389,12 +413,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
                         tmem_st8(trow + (c0 >> 1), pk);
                     }
                 };
+                // (with split_col: once P's first split_col columns are in TMEM the issuer starts P V on them)
+                auto half_ready = [&]() {
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&p_half[t]);
+                };
+                const int split = p.split_col;
                 tmem_ld32(trow, va);
                 for (int c0 = 0; c0 < Np_pad; c0 += 64) {
                     exp_step(va, vb, c0);
+                    if (c0 + 32 == split) half_ready();
                     if (c0 + 32 < Np_pad) exp_step(vb, va, c0 + 32);
+                    if (c0 + 64 == split) half_ready();
                 }
                 tmem_st_wait();
+            } else if (p.split_col) {
+                mbar_arrive(&p_half[t]);
             }
             tc_fence_before();
             if ((tid & 127) == 0) AT_TRACE(n, 14 + 8 * t);
@@ -484,6 +519,9 @@ int launch_attention_tc(const void* qkv, const int32_t* row_map, void* out, int 
     p.scale_log2 = scale * 1.4426950408889634f;
     p.o_outside = p.Np_pad <= 192;
     p.o_col = p.o_outside ? 192 : 128;
+    static const bool nosplit = getenv("RAJNI_ATTN_NOSPLIT") != nullptr;      // A/B switch
+    p.split_col = (p.o_outside && !nosplit && p.Np_pad >= 64) ? ((p.Np_pad / 2 + 31) & ~31) : 0;
+    if (p.split_col >= p.Np_pad) p.split_col = 0;
     // a plane holds the Q (or K, or V) rows of a stage; tile 1's Q rows / the second head start at row 128
     const int plane_rows = p.two_tiles ? p.Np_pad : 128 + p.Np_pad;
     p.plane_bytes = (plane_rows * 128 + 1023) & ~1023;

@@ -32,8 +32,9 @@ tot = collections.OrderedDict()
 for i, d in enumerate(byid.values()):
     n = short(d["name"])
     per.append(f"| {i} | {n} | {d['grid']} | {d[T]:.1f} | {d[RD]:.1f} | {d[WR]:.1f} | "
-               f"{d['gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed']:.1f} | {d['lts__throughput.avg.pct_of_peak_sustained_elapsed']:.1f} | "
-               f"{d['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed']:.1f} |")
+               f"{d.get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', d.get('dram__throughput.avg.pct_of_peak_sustained_elapsed', float('nan'))):.1f} | "
+               f"{d['lts__throughput.avg.pct_of_peak_sustained_elapsed']:.1f} | "
+               f"{d.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', float('nan')):.1f} |")
     cls = n.split("<")[0]
     m = re.match(r"gemm_bf16_kernel<(\d+), (\d), (\d), (\d)>", n)
     if m:
