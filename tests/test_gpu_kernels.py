@@ -269,6 +269,14 @@ def test_gelu_matches_erf(ops):
         worst = max(worst, ((got - ref).abs() / ref.abs().clamp_min(1e-3)).max().item())
         torch.testing.assert_close(got, ref, rtol=1e-4, atol=2e-6)
     print(f"gelu worst error relative to max(|ref|,1e-3): {worst:.2e}")
+    # the hot bf16 epilogue (packed fp32x2 evaluation of the same fit): within one bf16 rounding of the exact value
+    a2, w2 = torch.zeros(256, K), torch.zeros(256, K)
+    for i in range(0, 64, 7):
+        xb = x[i::64].contiguous()
+        out = ops.gemm(dev(a2, torch.bfloat16), dev(w2, torch.bfloat16), dev(xb), 256, 256, K, gelu=True)
+        ref = torch.nn.functional.gelu(xb.double())
+        got = out[i].cpu().double()
+        assert ((got - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-6).all()
 
 
 # ------------------------------------------------------------------ attention
