@@ -192,7 +192,8 @@ class RAJNIViTWrapper(nn.Module):
             self._forward_eager(x_static)                       # builds packs and workspace, warms every kernel
             torch.cuda.synchronize(x.device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # thread-local capture mode: a DataLoader's pin-memory thread may call into CUDA while this thread captures
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 y_static = self._forward_eager(x_static)
             entry = (graph, x_static, y_static, self._last_stats, self._last_keep_idx, wsig)
             self._graphs = {key: entry}                         # one shape resident, like the workspace

@@ -234,6 +234,22 @@ def test_evaluate_model(pkg):
     print("acc", acc2, "oracle acc", ref_acc)
 
 
+def test_evaluate_model_with_a_pinning_dataloader(pkg):
+    """A real DataLoader with worker + pin-memory threads (what rajni/run.py:72-76 builds) around the small-batch path, whose
+    first forward of each shape captures a CUDA graph: the capture must not mind the pin-memory thread's CUDA calls, and the
+    ragged last batch (a new shape) must work."""
+    from torch.utils.data import DataLoader, TensorDataset
+    model = build(pkg, "vit_micro_patch16_64", MICRO_SCHEDULE)
+    g = torch.Generator().manual_seed(3)
+    images, labels = make_images(44, 64, 5), torch.randint(0, 1000, (44,), generator=g)
+    loader = DataLoader(TensorDataset(images, labels), batch_size=8, shuffle=False, num_workers=2, pin_memory=True)
+    acc, ips = pkg.evaluate_model(model, loader, device="cuda", warmup=2, progress=False)
+    ref = build(pkg, "vit_micro_patch16_64", MICRO_SCHEDULE)
+    ref.use_cuda_graph = False
+    correct = sum(int((ref(images[i:i + 8].cuda()).argmax(dim=1).cpu() == labels[i:i + 8]).sum()) for i in range(0, 44, 8))
+    assert ips > 0 and abs(acc - 100.0 * correct / 44) < 1e-9
+
+
 def test_cli_synthetic(pkg, tmp_path, capsys):
     """python -m rajni_vit_b200.run with the reference's flags on synthetic batches: string-key schedule JSON prunes
     (normalised), --compare_base runs the un-pruned model on the same kernels."""
