@@ -282,7 +282,7 @@ def test_gelu_matches_erf(ops):
 # ------------------------------------------------------------------ attention
 @pytest.mark.parametrize("B,N,Np,H", [(2, 17, 17, 2), (3, 197, 197, 3), (2, 197, 173, 12), (2, 173, 152, 12),
                                       (2, 152, 121, 12), (2, 121, 87, 12), (1, 577, 507, 12), (2, 577, 577, 3), (1, 507, 446, 12), (3, 357, 257, 6), (2, 300, 300, 2), (1, 1000, 700, 2), (2, 64, 64, 1),
-                                      (2, 65, 65, 1), (2, 197, 2, 3)])
+                                      (2, 65, 65, 1), (2, 197, 2, 3), (2, 250, 250, 2), (1, 300, 240, 3), (2, 256, 256, 1), (3, 130, 129, 2), (2, 192, 192, 2), (2, 200, 193, 2)])
 def test_attention(ops, B, N, Np, H):
     C = H * 64
     qkv = make_qkv(B, N, H, 64, 500 + N + Np)
