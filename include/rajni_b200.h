@@ -112,9 +112,10 @@ int rajni_gemm_bf16(const void* A, const void* W, const float* bias, void* D,
  *   LN(x) W^T + b  =  rstd[m] * ( x (W.gamma)^T )[m,n]  -  rstd[m]*mean[m] * wsum[n]  +  ( b + W beta )[n]
  *
  * so the normalised activations never touch HBM.  Producer side (RAJNI_EPI_ROW_STATS, with the
- * bias+residual epilogue): for every stored row r the kernel writes, per 32-column chunk s,
- * row_stats[s*row_stats_ld + r] = (sum, sum of squares) of the bf16 values it stored in that slot;
- * rajni_gemm_row_stats_slots(N) = N/32 is the slot count for an N-column output.  Consumer side
+ * bias+residual epilogue): for every stored row r the kernel writes, per slot s of 64 columns (32 when
+ * N is not a multiple of 128), row_stats[s*row_stats_ld + r] = (sum, sum of squares) of the bf16 values
+ * it stored in that slot; rajni_gemm_row_stats_slots(N) is the slot count for an N-column output (the
+ * partition depends on N only, never on the tile shape or M, so results do not depend on the batch).  Consumer side
  * (RAJNI_EPI_LN_FOLD): A = x, W = bf16(W*gamma), bias = b + W beta, ln_wsum[n] = sum_k W'[n,k]; mean and the
  * biased variance of row m come from summing ln_slots partials at ln_stats[s*ln_stats_ld + m]; K is the
  * LayerNorm width.  Both need N % tile == 0 and 32-byte aligned rows (true for every ViT width). */

@@ -71,8 +71,9 @@ struct GemmParams {
     long long ln_stats_ld;
     int ln_slots;
     float ln_inv_k, ln_eps;
-    float2* row_stats;          // [N/32][row_stats_ld] partial (sum, sumsq) of the rows of D per 32-column chunk, or null
+    float2* row_stats;          // [N >> stat_shift][row_stats_ld] partial (sum, sumsq) of the rows of D per 32- or 64-column slot, or null
     long long row_stats_ld;
+    int stat_shift;             // 5 or 6: log2 of the slot width (rajni_gemm_row_stats_slots)
 };
 
 // Exact-erf GELU (timm nn.GELU) evaluated as x*Phi(x) with
@@ -300,6 +301,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
                 uint32_t va[32], vb[32];
                 tmem_ld32(taddr, va);
+                uint64_t sum2 = 0, sq2 = 0;                      // row statistics of the current slot (kRes)
+                const bool wide_slots = kRes && p.stat_shift == 6;   // 64-column slots: two chunks each (NCH is even then)
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
                     uint32_t (&cur)[32] = (ch & 1) ? vb : va;
@@ -317,7 +320,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                     }
                     uint32_t o[16];
-                    uint64_t sum2 = 0, sq2 = 0;                  // (0.f, 0.f): statistics of this 32-column chunk
+                    if (!wide_slots || !(ch & 1)) { sum2 = 0; sq2 = 0; }       // (0.f, 0.f): a new statistics slot starts here
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 bv = lds128(sb + (ch * 32 + j) * 4);
@@ -357,13 +360,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (valid) {
                         stg256(dptr + ch * 32, *reinterpret_cast<uint32_t(*)[8]>(&o[0]));
                         stg256(dptr + ch * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&o[8]));
-                        if (kRes && p.row_stats != nullptr) {
-                            // one slot per 32-column chunk of the row, whatever the tile width: the partition (and so the
+                        if (kRes && p.row_stats != nullptr && (!wide_slots || (ch & 1))) {
+                            // one slot per 32 (or 64) columns of the row, whatever the tile width: the partition (and so the
                             // rounding of the LayerNorm statistics) does not depend on the batch size
                             float a0, a1, b0, b1;
                             f2unpack(sum2, a0, a1);
                             f2unpack(sq2, b0, b1);
-                            p.row_stats[(long long)((ncol0 >> 5) + ch) * p.row_stats_ld + orow] = make_float2(a0 + a1, b0 + b1);
+                            p.row_stats[(long long)((ncol0 + ch * 32) >> p.stat_shift) * p.row_stats_ld + orow] = make_float2(a0 + a1, b0 + b1);
                         }
                     }
                 }
@@ -608,15 +611,15 @@ static int launch_gemm(const void* A, const void* W, GemmParams& p, cudaStream_t
 // `exact` (hot epilogues, no column-tail path): among the widths that divide N, the CTA-pair tiles (256 or 192 wide,
 // 256 rows) are preferred; between those two the one with fewer, fuller waves over the 74 CTA pairs wins
 // (e.g. N = 768, M = 44288: 173 x 3 tiles of 256 = 7.01 waves -> 8, but 173 x 4 tiles of 192 = 9.35 -> 10 x 3/4 = 7.5).
-static int pick_bn(int N, int M, bool exact) {
+static int pick_bn(int N, int M, bool exact, bool no192 = false) {
     if (exact) {
         static const char* force = getenv("RAJNI_GEMM_BN");                 // debugging aid: force a pair-tile width that divides N
-        if (force && M > BM && N % atoi(force) == 0 && (atoi(force) == 256 || atoi(force) == 192 || atoi(force) == 128)) return -atoi(force);
+        if (force && M > BM && N % atoi(force) == 0 && (atoi(force) == 256 || (atoi(force) == 192 && !no192) || atoi(force) == 128)) return -atoi(force);
         const bool pair = M > BM;
         int best = 0;
         double best_cost = 0;
         for (int bn : {256, 192, 128}) {
-            if (!pair || N % bn) continue;
+            if (!pair || N % bn || (no192 && bn == 192)) continue;
             const long long tiles = (long long)((M + 2 * BM - 1) / (2 * BM)) * (N / bn);
             const int pairs = num_sms() / 2;
             // the 192-wide tile re-reads A once more per row block: it has to save 8 % of the wave time to be chosen
@@ -638,9 +641,13 @@ static int pick_bn(int N, int M, bool exact) {
 
 using namespace rajni;
 
+// Slot width of the row statistics: 64 columns when N is a multiple of 128 (the producer then uses 256- or 128-wide tiles only,
+// whose epilogue warps own whole 64-column slots), else 32 (N = 192: the 192-wide tile's warps own 96 columns).
+static int stat_shift_for(int N) { return N % 128 == 0 ? 6 : 5; }
+
 extern "C" int rajni_gemm_row_stats_slots(int N) {
     if (N <= 0 || N % 64 != 0) return 0;            // ROW_STATS needs whole tiles
-    return N / 32;                                  // one slot per 32-column chunk
+    return N >> stat_shift_for(N);
 }
 
 extern "C" int rajni_gemm_bf16_ex(const rajni_gemm_args* a, void* stream) {
@@ -673,9 +680,11 @@ extern "C" int rajni_gemm_bf16_ex(const rajni_gemm_args* a, void* stream) {
     p.ln_eps = a->ln_eps;
     p.row_stats = (flags & RAJNI_EPI_ROW_STATS) ? reinterpret_cast<float2*>(a->row_stats) : nullptr;
     p.row_stats_ld = a->row_stats_ld;
+    p.stat_shift = stat_shift_for(N);
     const bool exact = (flags & (RAJNI_EPI_LN_FOLD | RAJNI_EPI_ROW_STATS)) != 0;
     RAJNI_REQUIRE(!exact || N % 64 == 0, RAJNI_EINVAL, "rajni_gemm_bf16: LN_FOLD / ROW_STATS need N %% 64 == 0 (N=%d)", N);
-    int bn = pick_bn(N, M, exact);                  // < 0: exact CTA-pair tile of width -bn
+    // (a producer of 64-column statistics slots cannot use the 192-wide tile)
+    int bn = pick_bn(N, M, exact, (flags & RAJNI_EPI_ROW_STATS) && stat_shift_for(N) == 6);   // < 0: exact CTA-pair tile of width -bn
     auto s = static_cast<cudaStream_t>(stream);
     // wide problems run as CTA pairs (256 x 256 tiles); narrow ones keep single-CTA tiles
     static const bool force_cg1 = getenv("RAJNI_GEMM_CG1") != nullptr;     // debugging aid
