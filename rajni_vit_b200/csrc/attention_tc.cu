@@ -6,10 +6,10 @@
 // One CTA per SM loops over work units.  A unit fills the two 128-row score tiles of the SM:
 //   Np > 128 : one (image, head); tile 0 = queries 0..127, tile 1 = queries 128..Np-1, shared K/V
 //   Np <= 128: two (image, head) pairs, one per tile, each with its own K/V
-// Roles (416 threads):
+// Roles (512 threads):
 //   warps 0-3 / 4-7 : softmax + epilogue of tile 0 / tile 1 (thread = query row = TMEM lane)
 //   warp 8          : tcgen05.mma issuer (one lane), an event loop over the two tiles
-//   warps 9-12      : loaders into 128-byte-swizzled shared memory, 2-4 stages deep, Q/K and V on separate
+//   warps 9-15      : loaders into 128-byte-swizzled shared memory, 2-4 stages deep, Q/K and V on separate
 //                     barriers.  Dense call (no row map): one TMA box per plane.  Gathered call: cp.async row
 //                     gather of the head's Q/K/V slices (128 B per token from arbitrary global rows), so the
 //                     kept-token gather needs no separate pass over HBM
@@ -30,8 +30,12 @@ namespace rajni {
 constexpr int kAtSoftmaxWarps = 8;
 constexpr int kAtMmaWarp = 8;
 constexpr int kAtLoaderWarp0 = 9;
-constexpr int kAtLoaderThreads = 128;
-constexpr int kAtThreads = (kAtSoftmaxWarps + 1) * 32 + kAtLoaderThreads;     // 416
+// 7 loader warps: 16 warps in all still leave 128 registers per thread, and the cp.async row gather of the pruned blocks is
+// bound by what each warp keeps in flight (4 loader warps: 119 us at 197 -> 173 tokens; the dense call needs one TMA thread)
+constexpr int kAtLoaderThreads = 224;
+constexpr int kAtLoaderGroups = kAtLoaderThreads / 8;                         // 8 lanes move one token's 128-byte head slice
+constexpr int kAtSlots = (128 + kAtLoaderGroups - 1) / kAtLoaderGroups;       // sweeps of the groups over 128 token rows
+constexpr int kAtThreads = (kAtSoftmaxWarps + 1) * 32 + kAtLoaderThreads;     // 512
 constexpr int kAtMaxStages = 4;
 constexpr int kAtTileCols = 256;
 constexpr int kAtOutStage = kAtSoftmaxWarps * 32 * 128;                        // output staging: 32 rows x 128 B per softmax warp
@@ -174,28 +178,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         const int grp = lt >> 3, chunk = lt & 7;
         const long long C3 = 3LL * p.C;
         const int nsub = p.two_tiles ? 1 : 2;
-        const int per_sub = p.two_tiles ? 16 : 8;                     // 16-token strides per sub-item (Np_pad <= 256 / 128)
         int stage = 0;
         uint32_t phase = 0;
         for (int n = 0; n < n_mine; ++n) {
             const int u = blockIdx.x + n * gridDim.x;
             // global row of every token this lane group moves: all index loads are issued together,
             // before (and independent of) the wait for the stage to drain
-            int grow[16], hcol[2];
+            int grow[2 * kAtSlots], hcol[2];
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
                 const int item = t < nsub ? unit_item(p, u, t) : -1;
                 const int b = item >= 0 ? item / p.H : 0;
                 hcol[t] = item >= 0 ? (item - b * p.H) * 64 + chunk * 8 : -1;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    // slot t*8+i: second sub-item, or (two_tiles) tokens 128.. of the one head
-                    const int j = grp + (p.two_tiles ? t * 8 + i : i) * (kAtLoaderThreads / 8);
+                for (int i = 0; i < kAtSlots; ++i) {
+                    // slot t*kAtSlots+i: second sub-item, or (two_tiles) the next sweeps over the one head
+                    const int j = grp + (p.two_tiles ? t * kAtSlots + i : i) * kAtLoaderGroups;
                     const int it2 = p.two_tiles ? unit_item(p, u, 0) : item;
                     const int b2 = p.two_tiles ? it2 / p.H : b;
                     int r = -1;
-                    if (it2 >= 0 && j < p.Np) r = p.row_map ? __ldg(p.row_map + (long long)b2 * p.Np + j) : b2 * p.N_src + j;
-                    grow[t * 8 + i] = r;
+                    if (it2 >= 0 && j < p.Np && (p.two_tiles || j < 128)) r = p.row_map ? __ldg(p.row_map + (long long)b2 * p.Np + j) : b2 * p.N_src + j;
+                    grow[t * kAtSlots + i] = r;
                 }
             }
             if (p.two_tiles) hcol[1] = hcol[0];
@@ -205,10 +208,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {                    // pass 0: Q and K (what S needs), pass 1: V
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int t = k >> 3;
-                    const int j = grp + (p.two_tiles ? k : (k & 7)) * (kAtLoaderThreads / 8);
-                    if (hcol[t] < 0 || j >= p.Np_pad || (!p.two_tiles && (k & 7) >= per_sub)) continue;
+                for (int k = 0; k < 2 * kAtSlots; ++k) {
+                    const int t = k / kAtSlots;
+                    const int j = grp + (p.two_tiles ? k : k - t * kAtSlots) * kAtLoaderGroups;
+                    if (hcol[t] < 0 || j >= p.Np_pad || (!p.two_tiles && j >= 128)) continue;
                     const bool ok = grow[k] >= 0;
                     const __nv_bfloat16* src = p.qkv + (long long)(ok ? grow[k] : 0) * C3 + hcol[t];
                     const int r = (p.two_tiles ? 0 : t * 128) + j;
