@@ -495,11 +495,10 @@ int make_tmap_bf16_2d_box(CUtensorMap* map, const void* base, long long rows, lo
 int make_tmap_bf16_3d_box(CUtensorMap* map, const void* base, long long batch, long long rows, long long cols, int box_rows);
 
 static int at_num_sms() {
-    static int n = 0;
+    static int n_dev[kMaxDevices] = {};          // per device: one process may drive several GPUs
+    int& n = n_dev[current_device()];
     if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, current_device());
         if (n <= 0) n = 148;
     }
     return n;

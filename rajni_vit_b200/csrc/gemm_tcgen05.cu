@@ -539,6 +539,22 @@ int make_tmap_bf16_3d_box(CUtensorMap* map, const void* base, long long batch, l
                   (int)r, batch, rows, cols);
     return 0;
 }
+// The same 3-d view for LOADS: box = box_rows x 64 columns of one batch entry; rows past the entry's `rows` are zero-filled,
+// so a box that starts in one image can never pull in the next image's values.
+int make_tmap_bf16_3d_ld(CUtensorMap* map, const void* base, long long batch, long long rows, long long cols, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    RAJNI_REQUIRE(fn != nullptr, RAJNI_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * (cuuint64_t)cols * 2};
+    cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RAJNI_REQUIRE(r == CUDA_SUCCESS, RAJNI_ECUDA, "cuTensorMapEncodeTiled (3d load) failed (%d) batch=%lld rows=%lld cols=%lld box_rows=%d",
+                  (int)r, batch, rows, cols, box_rows);
+    return 0;
+}
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols,
                       long long ld_elems, int box_rows) {
     return make_tmap_bf16_2d_box(map, base, rows, cols, ld_elems, 64, box_rows);
