@@ -1,10 +1,13 @@
 // a4: C-ABI entry of the attention over kept tokens (attention.py:42-54) and its dispatch to the three tcgen05 kernels.
 //
-//   Np_pad <= 224 : attention_pipe.cu  (role-pipelined: exp / max+epilogue / MMA / load warps, multi-buffered S in TMEM)
-//   Np     <= 256 : attention_tc.cu    (two score tiles of 256 columns; only token counts 225..256 land here)
-//   else          : attention_long.cu  (key blocks of 224, two passes; the 577-token configuration)
+//   dense, 128 < Np, Np_pad <= 224 : attention_pipe.cu  (role-pipelined: exp / epilogue / MMA / load warps, S multi-buffered in
+//                                    TMEM, half rows of S held in registers; per-image zero-filled TMA loads)
+//   other Np <= 256                : attention_tc.cu    (two score tiles of 256 columns; gathered calls and Np <= 128, where
+//                                    it is still the faster of the two: profiles/r2_attention_pipe.txt)
+//   else                           : attention_long.cu  (key blocks of 224, two passes; the 577-token configuration)
 //
-// RAJNI_ATTN_TC=1 sends every Np <= 256 call to attention_tc.cu (A/B timing against the round-1 kernel).
+// RAJNI_ATTN_TC=1 sends every Np <= 256 call to attention_tc.cu, RAJNI_ATTN_PIPE=1 every Np_pad <= 224 call to
+// attention_pipe.cu (A/B timing; the tests run both).
 #include <cstdlib>
 
 #include "common.cuh"
@@ -27,9 +30,10 @@ extern "C" int rajni_attention_fwd(const void* qkv, const int32_t* row_map, void
                   "rajni_attention_fwd: B=%d N_src=%d Np=%d C=%d H=%d (head dim must be 64)", B, N_src, Np, C, H);
     RAJNI_REQUIRE(row_map || N_src == Np, RAJNI_EINVAL, "rajni_attention_fwd: N_src != Np needs a row_map");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static const bool force_tc = getenv("RAJNI_ATTN_TC") != nullptr;
+    static const bool force_tc = getenv("RAJNI_ATTN_TC") != nullptr, force_pipe = getenv("RAJNI_ATTN_PIPE") != nullptr;
     int rc = 0;
-    if (!force_tc) rc = launch_attention_pipe(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, st);
+    if (force_pipe || (!force_tc && row_map == nullptr && Np > 128))
+        rc = launch_attention_pipe(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, st);
     if (rc == 0) rc = Np <= 256 ? launch_attention_tc(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, st)
                                 : launch_attention_long(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, st);
     if (rc == 0) {

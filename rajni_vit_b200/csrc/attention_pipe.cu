@@ -4,23 +4,25 @@
 //   token j of image b is read from global qkv row row_map[b*Np + j]     attention.py:42-43 (gather fused)
 //
 // One CTA per SM walks a sequence of 128-query TILES (an (image, head) item has one tile when Np <= 128, else two that
-// share K/V).  Each stage of the softmax has its own warps and the score tile is multi-buffered in TMEM, so the
-// MUFU-bound exponentials of tile g overlap the row maxima of tile g+1, the read-out of tile g-1 and the tensor pipe:
+// share K/V).  Each stage has its own warps and the score tile is multi-buffered in TMEM:
 //
-//   warps 0-7  EXP     thread = (query row, half of the key columns): p = exp2(s*scale*log2e - max), bf16 P written over
-//                      S in TMEM (each half in place behind its own read pointer), partial row sums to shared memory.
-//                      Two warps per scheduler keep MUFU.EX2 saturated (16/clk/SM); they do nothing else.
-//   warps 8-11 HELPER  thread = query row: (a) exact row maximum of S(g) as soon as the tensor pipe delivers it - one
-//                      tile AHEAD of the exp warps; (b) O(g) = P V out of TMEM, times 1/rowsum, bf16, swizzled shared
-//                      memory, one TMA store per warp (3-d map clipped at the image's Np rows).
+//   warps 0-7  EXP     thread = (query row, half of the key columns).  The thread pulls its WHOLE half row of S (<= 112
+//                      fp32) out of TMEM with one wait - a tcgen05.ld costs ~150 cycles alone and ~450 next to the tensor
+//                      pipe, whatever its size, so S is read exactly once and in one go (profiles/r2_pipe_probe.txt) - takes
+//                      the row maximum from registers, swaps it with the other half's through shared memory (one 64-thread
+//                      named barrier), then p = exp2(s*scale*log2e - max) -> bf16 P back into TMEM over S, partial row sum
+//                      to shared memory.  Exact two-pass softmax, like the reference.  (160 registers: setmaxnreg.)
+//   warps 8-11 EPILOGUE thread = query row: O(g) = P V out of TMEM, times 1/rowsum, bf16, swizzled shared memory, one TMA
+//                      store per warp (3-d map clipped at the image's Np rows).
 //   warp 12    MMA     one lane issues S(g) = Q K^T (SS, 4 k-steps) and O(g) = P V (TS: A = P from TMEM, V MN-major)
 //   warps 13-15 LOAD   dense call: one thread, three TMA boxes per item (3-d map: rows past the image are ZERO-filled, so
 //                      one image's Inf/NaN can never reach another's output); gathered call: cp.async row gather by row_map
 //
 // TMEM (512 columns): nbuf score buffers of s_stride columns (2 at Np_pad 208 ... 4 at Np_pad <= 96), then one or two
-// 64-column O buffers.  Softmax is exactly two-pass (true row maximum), like the reference.
-// Per 128x208 tile: MUFU floor 1664 cycles, tensor pipe 1800 (S 4x144 + PV 13x94, profiles/r1_mma_ldtm_mufu_probe.txt).
+// 64-column O buffers: S(g+1) is computed while the exp warps work on tile g and P(g-1) V runs.
 #include <cuda.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -36,8 +38,11 @@ constexpr int kApThreads = 512;
 constexpr int kApMaxStages = 4;
 constexpr int kApMaxBufs = 4;
 constexpr int kApSumSlots = 8;
+// Fetch the next tile's first 64 columns under the current tile's last exponentials.  Measured slower on B200 (the tensor pipe
+// spends ~130 cycles per P V k-step, so S(g+1) is rarely complete at the prefetch point and the probe only costs): off.
+constexpr bool kApPrefetch = false;
 constexpr int kApOutStage = 4 * 4096;                                          // 32 rows x 128 B per helper warp
-constexpr int kApAuxBytes = kApMaxBufs * 128 * 4 + kApSumSlots * 2 * 128 * 4;  // row maxima, partial row sums
+constexpr int kApAuxBytes = 2 * 2 * 128 * 4 + kApSumSlots * 2 * 128 * 4;       // half-row maxima (2 parities), partial row sums
 constexpr int kApBarBytes = 256;
 constexpr int kApSmemBudget = 227 * 1024 - 1024 - kApOutStage - kApAuxBytes - kApBarBytes;
 
@@ -72,13 +77,16 @@ __device__ __forceinline__ float ap_ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ void ap_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ float ap_fmax3(float a, float b, float c) {
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
-// Register re-partitioning between warpgroups (4 consecutive warps): the load/MMA warpgroup gives registers back, the
-// helper warpgroup (two 32-column TMEM loads in flight + its tile cursors) takes them.  8*128 + 4*184 + 4*72 = 2048 = 64 K / 32.
+// Register re-partitioning between warpgroups (4 consecutive warps): the load/MMA and the epilogue warpgroups give registers
+// back, the exp warpgroups (a half row of S = 112 registers) take them.  8*160 + 4*112 + 4*80 = 2048 = 64 K / 32.
 template <int N> __device__ __forceinline__ void ap_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(N)); }
 template <int N> __device__ __forceinline__ void ap_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(N)); }
 
@@ -108,23 +116,113 @@ struct ApCursor {
     }
 };
 
+// One exp-warp thread's share of a tile: the half row [cb, cb + 32*N32 + 16*HAS16) of S (TMEM row `sb`) -> P in place.
+// Straight-line for a given (N32, HAS16): no branch between the 16-column groups, so MUFU.EX2 never drains.
+//   Registers: group A = the first two 32-column pieces (s[0..63]), group B = the third piece (s[64..95]) and the
+//   16-column piece (s[96..111]).  The thread holds its WHOLE half row before the row maximum is taken (one wait for all
+//   loads: a tcgen05.ld costs 150-450 cycles whatever its size).  Columns >= Np (at most one partial group) are set to -inf
+//   up front, so neither the maximum nor exp2 needs a mask: exp2(-inf) = 0.
+//   Software pipeline across tiles: once group A's exponentials are packed and stored, group A of the NEXT tile (whose S
+//   the tensor pipe finished long ago, `next_bar`) is fetched into the freed registers under group B's exponentials
+//   (`have_a` tells the next call).  P pair k of a group overwrites the group's register k, consumed by then.
+// Returns the half row's sum of p.
+template <int N32, int HAS16>
+__device__ __forceinline__ float ap_exp_half(uint32_t (&s)[112], bool& have_a, uint32_t sb, uint32_t sb_next, uint64_t* next_bar,
+                                             uint32_t next_ph, int cb, int Np, float sl2, float* pm_mine, const float* pm_other,
+                                             int bar_id, bool trace_lane, int g) {
+    constexpr int NA = N32 < 2 ? N32 : 2;                                     // 32-column pieces of group A
+    constexpr int NB32 = N32 - NA;                                            // 0 or 1
+    constexpr int WB16 = NB32 ? 80 : 64;                                      // where the 16-column piece's P pairs go
+    if (!have_a) {
+#pragma unroll
+        for (int i = 0; i < NA; ++i) tmem_ld32(sb + cb + 32 * i, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * i]));
+    }
+    if (NB32) tmem_ld32(sb + cb + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+    if (HAS16) tmem_ld16(sb + cb + 32 * N32, *reinterpret_cast<uint32_t(*)[16]>(&s[96]));
+    tmem_ld_wait();
+    if (trace_lane) AP_TRACE(g, 4);
+    if (cb + 32 * N32 + 16 * HAS16 > Np) {                                    // this half holds the padding columns (rare path)
+#pragma unroll
+        for (int i = 0; i < 32 * N32; ++i) if (cb + i >= Np) s[i] = 0xff800000u;               // -inf
+        if (HAS16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (cb + 32 * N32 + i >= Np) s[96 + i] = 0xff800000u;
+        }
+    }
+    // ---- row maximum of this half (four independent chains), then of the row (the other half's through shared memory)
+    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < 32 * N32; i += 2) m4[(i >> 1) & 3] = ap_fmax3(m4[(i >> 1) & 3], __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+    if (HAS16) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) m4[(i >> 1) & 3] = ap_fmax3(m4[(i >> 1) & 3], __uint_as_float(s[96 + i]), __uint_as_float(s[97 + i]));
+    }
+    const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    *pm_mine = mx;
+    ap_bar_sync(bar_id, 64);                                                  // the two warps that share these 32 rows
+    const float mb = fmaxf(mx, *pm_other) * sl2;
+    if (trace_lane) AP_TRACE(g, 5);
+    float sum0 = 0.f, sum1 = 0.f;
+    // p = exp2(s * scale * log2e - max) for R0..R0+16*NCH -> bf16 pairs at W0..
+    auto exp_run = [&](auto r0_c, auto w0_c, auto n_c) {
+        constexpr int R0 = decltype(r0_c)::value, W0 = decltype(w0_c)::value, N = decltype(n_c)::value;
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+            const float e0 = ap_ex2(fmaf(__uint_as_float(s[R0 + j]), sl2, -mb));
+            const float e1 = ap_ex2(fmaf(__uint_as_float(s[R0 + j + 1]), sl2, -mb));
+            sum0 += e0;
+            sum1 += e1;
+            s[W0 + (j >> 1)] = float2_to_bf16x2(e0, e1);
+        }
+    };
+    using std::integral_constant;
+    // ---- group A
+    exp_run(integral_constant<int, 0>{}, integral_constant<int, 0>{}, integral_constant<int, 32 * NA>{});
+    if (NA == 2) tmem_st32(sb + cb, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+    else if (NA == 1) tmem_st16(sb + cb, *reinterpret_cast<uint32_t(*)[16]>(&s[0]));
+    have_a = false;
+    if (NB32 + HAS16 > 0) {
+        // ---- group B, first 16 columns; then group A of the next tile into the freed registers; then the rest of B
+        constexpr int RB = NB32 ? 64 : 96;
+        exp_run(integral_constant<int, RB>{}, integral_constant<int, 64>{}, integral_constant<int, 16>{});
+        if (kApPrefetch && NA > 0 && next_bar != nullptr && ap_test_uniform(next_bar, next_ph)) {
+            tmem_st_wait();                                                   // P of group A has left its registers
+            tc_fence_after();
+#pragma unroll
+            for (int i = 0; i < NA; ++i) tmem_ld32(sb_next + cb + 32 * i, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * i]));
+            have_a = true;
+        }
+        if (NB32) {
+            exp_run(integral_constant<int, 80>{}, integral_constant<int, 72>{}, integral_constant<int, 16>{});
+            tmem_st16(sb + cb + 32, *reinterpret_cast<uint32_t(*)[16]>(&s[64]));
+            if (HAS16) {
+                exp_run(integral_constant<int, 96>{}, integral_constant<int, WB16>{}, integral_constant<int, 16>{});
+                tmem_st8(sb + cb + 48, *reinterpret_cast<uint32_t(*)[8]>(&s[WB16]));
+            }
+        } else {
+            tmem_st8(sb + cb + 16 * N32, *reinterpret_cast<uint32_t(*)[8]>(&s[64]));
+        }
+    }
+    if (trace_lane) AP_TRACE(g, 10);
+    return sum0 + sum1;
+}
+
 __global__ void __launch_bounds__(kApThreads, 1)
 attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, const AttnPipeParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const int stage_bytes = 3 * p.plane_bytes;
-    // [stages][Q|K|V planes] [output staging: 4 warps x 4 KB] [row maxima][partial row sums][barriers]
+    // [stages][Q|K|V planes] [output staging: 4 warps x 4 KB] [half-row maxima][partial row sums][barriers]
     // (a tile's Q operand is read as 128 rows from row 0 / 128 of the Q plane: the over-read lands in the stage's K plane)
     const uint32_t out_stage0 = smem_base + p.stages * stage_bytes;
-    float* mrow = reinterpret_cast<float*>(smem_gen + p.stages * stage_bytes + kApOutStage);     // [nbuf][128]  max * scale * log2e
-    float* sums = mrow + kApMaxBufs * 128;                                                         // [8 slots][2 halves][128]
+    float* pmax = reinterpret_cast<float*>(smem_gen + p.stages * stage_bytes + kApOutStage);     // [2 parities][2 halves][128] half-row maxima
+    float* sums = pmax + 2 * 2 * 128;                                                              // [8 slots][2 halves][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sums + kApSumSlots * 2 * 128);
     uint64_t* qk_full = bars;                        // [4] loader -> MMA
     uint64_t* v_full = bars + 4;                     // [4] loader -> MMA
     uint64_t* stage_empty = bars + 8;                // [4] MMA -> loader (tcgen05.commit after the item's last P V)
-    uint64_t* s_full = bars + 12;                    // [4 bufs] MMA -> helpers (S ready)
-    uint64_t* m_ready = bars + 16;                   // [4 bufs] helpers -> exp warps (row maxima in shared memory)
+    uint64_t* s_full = bars + 12;                    // [4 bufs] MMA -> exp warps (S ready)
     uint64_t* p_full = bars + 20;                    // [4 bufs] exp warps -> MMA (P in TMEM)
     uint64_t* o_full = bars + 24;                    // [2] MMA -> helpers
     uint64_t* o_empty = bars + 26;                   // [2] helpers -> MMA (O read out)
@@ -143,7 +241,6 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
             }
             for (int i = 0; i < kApMaxBufs; ++i) {
                 mbar_init(&s_full[i], 1);
-                mbar_init(&m_ready[i], 4);           // one arrival per helper warp
                 mbar_init(&p_full[i], 8);            // one arrival per exp warp
             }
             for (int i = 0; i < 2; ++i) {
@@ -165,7 +262,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
 
     if (warp >= kApMmaWarp) {
       // warpgroup 3 (MMA issuer + loaders) hands registers back: ONE setmaxnreg site for its four warps
-      ap_reg_dec<72>();
+      ap_reg_dec<80>();
       if (warp >= kApLoaderWarp0 && p.row_map == nullptr) {
         // ================= dense loader: one TMA box per plane; rows past the image's N_src are zero-filled =================
         if (tid == kApLoaderWarp0 * 32) {
@@ -235,202 +332,152 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
         if (lane == 0) {
             const uint32_t idesc_s = umma_idesc_bf16(128, Np_pad, 0, 0);
             const uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);          // B = V is MN-major
-            const int nk = Np_pad / 16;
+            const int nk = Np_pad / 16, nk0 = p.split / 16;
             const uint64_t qd0 = umma_desc_sw128(smem_base, 16, 1024);
             const uint64_t kd0 = umma_desc_sw128(smem_base + p.plane_bytes, 16, 1024);
             const uint64_t vd0 = umma_desc_sw128(smem_base + 2 * p.plane_bytes, 16, 1024);
             ApCursor s, v;
-            int ob = 0, o_use0 = 0, o_use1 = 0;                               // O buffer of the next PV; how often each has been used
-            while (v.g < G) {
-                bool did = false;
-                if (s.g < G && s.g - v.g < p.nbuf && mbar_test(&qk_full[s.stage], s.stage_ph)) {
-                    tc_fence_after();
-                    AP_TRACE(s.g, 0);
-                    const uint64_t qd = qd0 + (uint64_t)((s.stage * stage_bytes + s.j * (128 * 128)) >> 4);
-                    const uint64_t kd = kd0 + (uint64_t)((s.stage * stage_bytes) >> 4);
-                    const uint32_t d = tmem_base + s.buf * p.s_stride;
+            int ob = 0;
+            uint32_t o_ph0 = 1, o_ph1 = 1;                                    // parity of the o_empty phase the next PV waits for
+            // (a fresh barrier passes a wait on parity 1: the first use of each O buffer does not wait)
+            auto issue_s = [&]() {
+                mbar_wait(&qk_full[s.stage], s.stage_ph);
+                tc_fence_after();
+                AP_TRACE(s.g, 0);
+                const uint64_t qd = qd0 + (uint64_t)((s.stage * stage_bytes + s.j * (128 * 128)) >> 4);
+                const uint64_t kd = kd0 + (uint64_t)((s.stage * stage_bytes) >> 4);
+                const uint32_t d = tmem_base + s.buf * p.s_stride;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(d, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_s, k != 0);
-                    umma_commit(&s_full[s.buf]);
-                    AP_TRACE(s.g, 1);
-                    s.advance(p);
-                    did = true;
-                }
-                const int o_use = ob ? o_use1 : o_use0;
-                if (v.g < s.g && mbar_test(&p_full[v.buf], v.buf_ph) && mbar_test(&v_full[v.stage], v.stage_ph) &&
-                    (o_use == 0 || mbar_test(&o_empty[ob], (o_use - 1) & 1))) {
-                    tc_fence_after();
-                    AP_TRACE(v.g, 2);
-                    const uint64_t vd = vd0 + (uint64_t)((v.stage * stage_bytes) >> 4);
-                    const uint32_t pb = tmem_base + v.buf * p.s_stride;
-                    const uint32_t d = tmem_base + p.o_col + ob * 64;
-                    for (int k = 0; k < nk; ++k) {
-                        const int key0 = k * 16;
-                        const uint32_t a = pb + (key0 < p.split ? (key0 >> 1) : p.split + ((key0 - p.split) >> 1));
-                        umma_bf16_ts(d, a, vd + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0);
-                    }
-                    umma_commit(&o_full[ob]);
-                    if (v.j == p.tpi - 1) umma_commit(&stage_empty[v.stage]);     // the item's last product: the stage may be refilled
-                    AP_TRACE(v.g, 3);
-                    if (ob) ++o_use1; else ++o_use0;
-                    if (++ob == p.n_obuf) ob = 0;
-                    v.advance(p);
-                    did = true;
-                }
-                if (!did) __nanosleep(20);
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(d, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_s, k != 0);
+                umma_commit(&s_full[s.buf]);
+                AP_TRACE(s.g, 1);
+                s.advance(p);
+            };
+            // Fixed issue order with BLOCKING waits (a polling issuer takes issue slots from the exp warps of its scheduler):
+            //   S(0) .. S(nbuf-1),  then  PV(g), S(g+nbuf)  for every tile g
+            for (int i = 0; i < p.nbuf && s.g < G; ++i) issue_s();
+            for (; v.g < G; v.advance(p)) {
+                mbar_wait(&p_full[v.buf], v.buf_ph);
+                mbar_wait(&v_full[v.stage], v.stage_ph);
+                mbar_wait(&o_empty[ob], ob ? o_ph1 : o_ph0);
+                tc_fence_after();
+                AP_TRACE(v.g, 2);
+                const uint64_t vd = vd0 + (uint64_t)((v.stage * stage_bytes) >> 4);
+                const uint32_t pb = tmem_base + v.buf * p.s_stride;
+                const uint32_t d = tmem_base + p.o_col + ob * 64;
+                // P of key columns [0, split) sits at the buffer's start, P of [split, Np_pad) at column `split`
+                uint64_t vdk = vd;
+                for (int k = 0; k < nk0; ++k, vdk += (2048 >> 4)) umma_bf16_ts(d, pb + k * 8, vdk, idesc_o, k != 0);
+                for (int k = 0; k < nk - nk0; ++k, vdk += (2048 >> 4)) umma_bf16_ts(d, pb + p.split + k * 8, vdk, idesc_o, 1);
+                AP_TRACE(v.g, 12);
+                umma_commit(&o_full[ob]);
+                if (v.j == p.tpi - 1) umma_commit(&stage_empty[v.stage]);     // the item's last product: the stage may be refilled
+                AP_TRACE(v.g, 3);
+                if (ob) o_ph1 ^= 1; else o_ph0 ^= 1;
+                if (++ob == p.n_obuf) ob = 0;
+                if (s.g < G) issue_s();                                       // into the buffer this PV has just released
             }
         }
       }
     } else if (warp >= kApHelpWarp0) {
-        // ================= helpers: row maxima one tile ahead of the exp warps, and the O epilogue =================
-        ap_reg_inc<184>();
+        // ================= epilogue warps: O(g) = P V out of TMEM, normalise, store =================
+        ap_reg_dec<112>();
         const int hq = warp - kApHelpWarp0;                                  // TMEM lane quadrant
         const int row = hq * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(hq * 32) << 16);
-        const float sl2 = p.scale_log2;
         const uint32_t s_out = out_stage0 + hq * 4096;
-        ApCursor m, e;                                                        // next tile whose maxima / whose O is due
-        int ob = 0;
+        ApCursor e;
+        int ob = 0, slot = 0;
         uint32_t o_ph0 = 0, o_ph1 = 0;
-        int slot = 0;
-        while (e.g < G) {
-            if (m.g < G && ap_test_uniform(&s_full[m.buf], m.buf_ph)) {
-                // ---- (a) exact row maximum of S(m.g)
-                tc_fence_after();
-                if (hq == 0 && lane == 0) AP_TRACE(m.g, 4);
-                if (m.j * 128 + hq * 32 < Np) {
-                    const uint32_t sb = lane_base + m.buf * p.s_stride;
-                    uint32_t va[32], vb[32];
-                    float mx = -INFINITY;
-                    auto max32 = [&](const uint32_t (&cur)[32], int c0) {
-                        if (c0 + 32 <= Np) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 2) mx = ap_fmax3(mx, __uint_as_float(cur[j]), __uint_as_float(cur[j + 1]));
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) if (c0 + j < Np) mx = fmaxf(mx, __uint_as_float(cur[j]));
-                        }
-                    };
-                    for (int c0 = 0; c0 < Np; c0 += 64) {
-                        // two loads in flight, both unconditional (the second may read past Np: still inside the 512 columns,
-                        // masked in max32)
-                        tmem_ld32(sb + c0, va);
-                        tmem_ld32(sb + c0 + 32, vb);
-                        tmem_ld_wait();
-                        max32(va, c0);
-                        max32(vb, c0 + 32);
-                    }
-                    mrow[m.buf * 128 + row] = mx * sl2;
-                    tc_fence_before();
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&m_ready[m.buf]);
-                if (hq == 0 && lane == 0) AP_TRACE(m.g, 5);
-                m.advance(p);
-                continue;
+        for (; e.g < G; e.advance(p)) {
+            mbar_wait(&o_full[ob], ob ? o_ph1 : o_ph0);
+            tc_fence_after();
+            if (hq == 0 && lane == 0) AP_TRACE(e.g, 6);
+            const bool live = e.j * 128 + hq * 32 < Np;
+            uint32_t o0[32], o1[32];
+            if (live) {
+                const uint32_t ocol = lane_base + p.o_col + ob * 64;
+                tmem_ld32(ocol, o0);
+                tmem_ld32(ocol + 32, o1);
+                tmem_ld_wait();
+                tc_fence_before();
             }
-            if (e.g < m.g && ap_test_uniform(&o_full[ob], ob ? o_ph1 : o_ph0)) {
-                // ---- (b) O(e.g) = P V is complete: normalise, store
-                tc_fence_after();
-                if (hq == 0 && lane == 0) AP_TRACE(e.g, 6);
-                const bool live = e.j * 128 + hq * 32 < Np;
-                uint32_t o0[32], o1[32];
-                if (live) {
-                    const uint32_t ocol = lane_base + p.o_col + ob * 64;
-                    tmem_ld32(ocol, o0);
-                    tmem_ld32(ocol + 32, o1);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_empty[ob]);
+            if (live) {
+                const float inv = 1.f / (sums[(slot * 2 + 0) * 128 + row] + sums[(slot * 2 + 1) * 128 + row]);
+                if (lane == 0) bulk_wait_group_read<0>();                 // the previous store has read the staging buffer
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&o_empty[ob]);
-                if (live) {
-                    const float inv = 1.f / (sums[(slot * 2 + 0) * 128 + row] + sums[(slot * 2 + 1) * 128 + row]);
-                    if (lane == 0) bulk_wait_group_read<0>();                 // the previous store has read the staging buffer
-                    __syncwarp();
-                    const uint32_t srow = s_out + lane * 128;
+                const uint32_t srow = s_out + lane * 128;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const uint32_t (&src)[32] = c < 4 ? o0 : o1;
-                        const int j = (c & 3) * 8;
-                        ap_sts128(srow + ((c ^ (lane & 7)) << 4),
-                                  float2_to_bf16x2(__uint_as_float(src[j]) * inv, __uint_as_float(src[j + 1]) * inv),
-                                  float2_to_bf16x2(__uint_as_float(src[j + 2]) * inv, __uint_as_float(src[j + 3]) * inv),
-                                  float2_to_bf16x2(__uint_as_float(src[j + 4]) * inv, __uint_as_float(src[j + 5]) * inv),
-                                  float2_to_bf16x2(__uint_as_float(src[j + 6]) * inv, __uint_as_float(src[j + 7]) * inv));
-                    }
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int item = ap_item(p, e.n);
-                        const int b = item / p.H, h = item - b * p.H;
-                        tma_store_3d(&tmap_out, s_out, h * 64, e.j * 128 + hq * 32, b);
-                        bulk_commit_group();
-                    }
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t (&src)[32] = c < 4 ? o0 : o1;
+                    const int j = (c & 3) * 8;
+                    ap_sts128(srow + ((c ^ (lane & 7)) << 4),
+                              float2_to_bf16x2(__uint_as_float(src[j]) * inv, __uint_as_float(src[j + 1]) * inv),
+                              float2_to_bf16x2(__uint_as_float(src[j + 2]) * inv, __uint_as_float(src[j + 3]) * inv),
+                              float2_to_bf16x2(__uint_as_float(src[j + 4]) * inv, __uint_as_float(src[j + 5]) * inv),
+                              float2_to_bf16x2(__uint_as_float(src[j + 6]) * inv, __uint_as_float(src[j + 7]) * inv));
                 }
-                if (hq == 0 && lane == 0) AP_TRACE(e.g, 7);
-                if (ob) o_ph1 ^= 1; else o_ph0 ^= 1;
-                if (++ob == p.n_obuf) ob = 0;
-                if (++slot == kApSumSlots) slot = 0;
-                e.advance(p);
-                continue;
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    const int item = ap_item(p, e.n);
+                    const int b = item / p.H, h = item - b * p.H;
+                    tma_store_3d(&tmap_out, s_out, h * 64, e.j * 128 + hq * 32, b);
+                    bulk_commit_group();
+                }
             }
-            __nanosleep(20);
+            if (hq == 0 && lane == 0) AP_TRACE(e.g, 7);
+            if (ob) o_ph1 ^= 1; else o_ph0 ^= 1;
+            if (++ob == p.n_obuf) ob = 0;
+            if (++slot == kApSumSlots) slot = 0;
         }
         if (lane == 0) bulk_wait_group<0>();                                  // output stores complete before the CTA retires
     } else {
         // ================= exp warps: thread = (query row, half of the key columns) =================
+        ap_reg_inc<160>();
         const int q = warp & 3, half = warp >> 2;
         const int row = q * 32 + lane;
-        const int cb = half ? p.split : 0, ce = half ? Np_pad : p.split;
+        const int cb = half ? p.split : 0;
+        const int ncol = (half ? Np_pad : p.split) - cb;                      // multiple of 16, <= 112
+        const int nch = ncol >> 4;                                            // 16-column groups of this half (0..7)
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         const float sl2 = p.scale_log2;
         ApCursor c;
         int slot = 0;
+        uint32_t s[112];                                                      // the half row of S; group A may hold the NEXT tile's
+        bool have_a = false;
         for (; c.g < G; c.advance(p)) {
-            mbar_wait(&m_ready[c.buf], c.buf_ph);
+            if (!have_a) mbar_wait(&s_full[c.buf], c.buf_ph);                 // (a prefetched group A has seen this phase complete)
             if (warp == 0 && lane == 0) AP_TRACE(c.g, 8);
             if (c.j * 128 + q * 32 < Np) {
-                const float mb = mrow[c.buf * 128 + row];
                 tc_fence_after();
                 const uint32_t sb = lane_base + c.buf * p.s_stride;
-                // P chunk of S columns [c0, c0+16) lands on columns cb + (c0-cb)/2 ..+8: behind this thread's read pointer
-                uint32_t va[16], vb[16];
-                float sum0 = 0.f, sum1 = 0.f;
-                auto exp16 = [&](const uint32_t (&cur)[16], uint32_t (&nxt)[16], int c0) {
-                    tmem_ld_wait();
-                    if (c0 + 16 < ce) tmem_ld16(sb + c0 + 16, nxt);
-                    uint32_t pk[8];
-                    if (c0 + 16 <= Np) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            const float e0 = ap_ex2(fmaf(__uint_as_float(cur[j]), sl2, -mb));
-                            const float e1 = ap_ex2(fmaf(__uint_as_float(cur[j + 1]), sl2, -mb));
-                            sum0 += e0;
-                            sum1 += e1;
-                            pk[j >> 1] = float2_to_bf16x2(e0, e1);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            const float e0 = (c0 + j < Np) ? ap_ex2(fmaf(__uint_as_float(cur[j]), sl2, -mb)) : 0.f;
-                            const float e1 = (c0 + j + 1 < Np) ? ap_ex2(fmaf(__uint_as_float(cur[j + 1]), sl2, -mb)) : 0.f;
-                            sum0 += e0;
-                            sum1 += e1;
-                            pk[j >> 1] = float2_to_bf16x2(e0, e1);
-                        }
-                    }
-                    tmem_st8(sb + cb + ((c0 - cb) >> 1), pk);
-                };
-                if (cb < ce) {
-                    tmem_ld16(sb + cb, va);
-                    for (int c0 = cb; c0 < ce; c0 += 32) {
-                        exp16(va, vb, c0);
-                        if (c0 + 16 < ce) exp16(vb, va, c0 + 16);
-                    }
+                ApCursor nx = c;
+                nx.advance(p);
+                const bool next_live = nx.g < G && nx.j * 128 + q * 32 < Np;
+                uint64_t* next_bar = next_live ? &s_full[nx.buf] : nullptr;
+                const uint32_t sb_next = lane_base + nx.buf * p.s_stride;
+                float* pm = pmax + (c.g & 1) * 256;
+                float* pm_mine = pm + half * 128 + row;
+                const float* pm_other = pm + (half ^ 1) * 128 + row;
+                const bool tl = warp == 0 && lane == 0;
+                float sum;
+#define AP_HALF(N32_, H16_) ap_exp_half<N32_, H16_>(s, have_a, sb, sb_next, next_bar, nx.buf_ph, cb, Np, sl2, pm_mine, pm_other, 1 + q, tl, c.g)
+                switch (nch) {                                                // warp-uniform: one straight-line body per width
+                    case 7: sum = AP_HALF(3, 1); break;
+                    case 6: sum = AP_HALF(3, 0); break;
+                    case 5: sum = AP_HALF(2, 1); break;
+                    case 4: sum = AP_HALF(2, 0); break;
+                    case 3: sum = AP_HALF(1, 1); break;
+                    case 2: sum = AP_HALF(1, 0); break;
+                    case 1: sum = AP_HALF(0, 1); break;
+                    default: sum = AP_HALF(0, 0); break;
                 }
-                sums[(slot * 2 + half) * 128 + row] = sum0 + sum1;
+#undef AP_HALF
+                sums[(slot * 2 + half) * 128 + row] = sum;
                 tmem_st_wait();
                 tc_fence_before();
             }

@@ -111,14 +111,14 @@ int main(int argc, char** argv) {
         if (B == 256 && getenv("AP_TRACE")) {
             static long long tr[64 * 16];
             cudaMemcpyFromSymbol(tr, rajni::g_ap_trace, sizeof(tr));
-            const char* names[10] = {"S:beg", "S:end", "PV:beg", "PV:end", "max:beg", "max:end", "epi:beg", "epi:end", "exp:beg", "exp:end"};
+            const char* names[13] = {"S:beg", "S:end", "PV:beg", "PV:end", "ld:done", "max:done", "epi:beg", "epi:end", "exp:beg", "exp:end", "math:end", "PV:k0", "PV:k1"};
             const long long t0 = tr[0];
             printf("tile");
-            for (int s = 0; s < 10; ++s) printf(" %8s", names[s]);
+            for (int s = 0; s < 13; ++s) printf(" %8s", names[s]);
             printf("\n");
             for (int g = 0; g < 24; ++g) {
                 printf("%4d", g);
-                for (int s = 0; s < 10; ++s) printf(" %8lld", tr[g * 16 + s] ? tr[g * 16 + s] - t0 : -1);
+                for (int s = 0; s < 13; ++s) printf(" %8lld", tr[g * 16 + s] ? tr[g * 16 + s] - t0 : -1);
                 printf("\n");
             }
         }
