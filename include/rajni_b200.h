@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RAJNI_ABI_VERSION 6
+#define RAJNI_ABI_VERSION 7
 
 enum {
     RAJNI_OK = 0,
@@ -137,6 +137,12 @@ int rajni_gemm_row_stats_slots(int N);
  * reverse != 0: process the images last-to-first (L2 reuse hint, see RAJNI_HINT_REVERSE_M). */
 int rajni_attention_fwd(const void* qkv, const int32_t* row_map, void* out,
                         int B, int N_src, int Np, int C, int H, float scale, int reverse, void* stream);
+/* The same call with the kernel chosen by the caller (tests and A/B timing; results agree within bf16 rounding):
+ * AUTO = what rajni_attention_fwd picks; PIPE = role-pipelined kernel (Np_pad <= 224); TC = two-tile kernel (Np <= 256);
+ * LONG = key-block kernel (built for Np > 256).  A kernel asked for a shape it does not cover returns RAJNI_EINVAL. */
+enum { RAJNI_ATTN_AUTO = 0, RAJNI_ATTN_PIPE = 1, RAJNI_ATTN_TC = 2, RAJNI_ATTN_LONG = 3 };
+int rajni_attention_fwd_ex(const void* qkv, const int32_t* row_map, void* out,
+                           int B, int N_src, int Np, int C, int H, float scale, int reverse, int impl, void* stream);
 
 /* ---- a8: patch-embed front end (model.py:31-37)
  * im2col: images [B,3,S,S] (image_dtype: RAJNI_IMG_BF16 / _F32 / _U8) -> cols [B*P, 3*p*p] bf16

@@ -6,7 +6,8 @@ forward path behind the reference's API (rajni/__init__.py:1-2):
 PyTorch provides device memory, streams and torch.distributed; all arithmetic runs in
 hand-written CUDA kernels behind the C ABI of include/rajni_b200.h.
 """
+from .checkpoint import load_checkpoint
 from .eval import evaluate_model
 from .wrapper import RAJNIAttention, RAJNIViTWrapper, compute_importance
 
-__all__ = ["RAJNIViTWrapper", "RAJNIAttention", "compute_importance", "evaluate_model"]
+__all__ = ["RAJNIViTWrapper", "RAJNIAttention", "compute_importance", "evaluate_model", "load_checkpoint"]

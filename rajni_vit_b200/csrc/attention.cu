@@ -23,22 +23,36 @@ int launch_attention_long(const void* qkv, const int32_t* row_map, void* out, in
 
 using namespace rajni;
 
-extern "C" int rajni_attention_fwd(const void* qkv, const int32_t* row_map, void* out,
-                                   int B, int N_src, int Np, int C, int H, float scale, int reverse, void* stream) {
+static int attention_dispatch(const void* qkv, const int32_t* row_map, void* out, int B, int N_src, int Np, int C, int H,
+                              float scale, int reverse, int impl, cudaStream_t st) {
     RAJNI_REQUIRE(qkv && out, RAJNI_EINVAL, "rajni_attention_fwd: null pointer");
     RAJNI_REQUIRE(B > 0 && Np > 0 && N_src >= Np && H > 0 && C == H * 64, RAJNI_EINVAL,
                   "rajni_attention_fwd: B=%d N_src=%d Np=%d C=%d H=%d (head dim must be 64)", B, N_src, Np, C, H);
     RAJNI_REQUIRE(row_map || N_src == Np, RAJNI_EINVAL, "rajni_attention_fwd: N_src != Np needs a row_map");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static const bool force_tc = getenv("RAJNI_ATTN_TC") != nullptr, force_pipe = getenv("RAJNI_ATTN_PIPE") != nullptr;
+    RAJNI_REQUIRE(impl >= RAJNI_ATTN_AUTO && impl <= RAJNI_ATTN_LONG, RAJNI_EINVAL, "rajni_attention_fwd_ex: impl %d", impl);
+    if (impl == RAJNI_ATTN_AUTO) {
+        static const bool force_tc = getenv("RAJNI_ATTN_TC") != nullptr, force_pipe = getenv("RAJNI_ATTN_PIPE") != nullptr;
+        const int np_pad = (Np + 15) & ~15;
+        if (np_pad <= 224 && (force_pipe || (!force_tc && row_map == nullptr && Np > 128))) impl = RAJNI_ATTN_PIPE;
+        else impl = Np <= 256 ? RAJNI_ATTN_TC : RAJNI_ATTN_LONG;
+    }
     int rc = 0;
-    if (force_pipe || (!force_tc && row_map == nullptr && Np > 128))
-        rc = launch_attention_pipe(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, st);
-    if (rc == 0) rc = Np <= 256 ? launch_attention_tc(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, st)
-                                : launch_attention_long(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, st);
+    if (impl == RAJNI_ATTN_PIPE) rc = launch_attention_pipe(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, st);
+    else if (impl == RAJNI_ATTN_TC) rc = launch_attention_tc(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, st);
+    else rc = launch_attention_long(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, st);
     if (rc == 0) {
-        set_error("rajni_attention_fwd: no kernel for Np=%d", Np);
+        set_error("rajni_attention_fwd: kernel %d does not cover Np=%d", impl, Np);
         return RAJNI_EINVAL;
     }
     return rc < 0 ? rc : RAJNI_OK;
+}
+
+extern "C" int rajni_attention_fwd(const void* qkv, const int32_t* row_map, void* out,
+                                   int B, int N_src, int Np, int C, int H, float scale, int reverse, void* stream) {
+    return attention_dispatch(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, RAJNI_ATTN_AUTO, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rajni_attention_fwd_ex(const void* qkv, const int32_t* row_map, void* out,
+                                      int B, int N_src, int Np, int C, int H, float scale, int reverse, int impl, void* stream) {
+    return attention_dispatch(qkv, row_map, out, B, N_src, Np, C, H, scale, reverse, impl, static_cast<cudaStream_t>(stream));
 }

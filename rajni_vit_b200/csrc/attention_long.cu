@@ -118,8 +118,7 @@ attention_long_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 
     if (warp >= kAlLoaderWarp0 && p.row_map == nullptr) {
         // ================= dense loader: the head's tokens are consecutive global rows -> TMA boxes, one thread =================
-        // (rows past the image's Np belong to the next image - finite values, masked by the softmax - or lie past the
-        //  tensor and are zero-filled)
+        // (3-d map [image][token][3C]: rows past the image's tokens are zero-filled, never the next image's)
         if (tid == kAlLoaderWarp0 * 32) {
             tma_prefetch_desc(&tmap_q);
             tma_prefetch_desc(&tmap_kv);
@@ -133,15 +132,15 @@ attention_long_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 mbar_wait(&q_empty[qb], ((n >> 1) & 1) ^ 1);
                 AL_TRACE(n, 0);
                 mbar_expect_tx(&q_full[qb], kAlQBytes);
-                tma_load_2d(smem_gen + qb * kAlQBytes, &tmap_q, &q_full[qb], h * 64, b * p.N_src + qt * 128);
+                tma_load_3d(smem_gen + qb * kAlQBytes, &tmap_q, &q_full[qb], h * 64, qt * 128, b);      // rows past the image: zero-filled
                 for (int pass = 0; pass < 2; ++pass) {
                     for (int j = 0; j < nb; ++j, ++rs) {
                         const int stage = rs % kAlStages;
                         mbar_wait(&empty_bar[stage], ((rs / kAlStages) & 1) ^ 1);
                         uint8_t* sk = smem_gen + 2 * kAlQBytes + stage * kAlStageBytes;
                         mbar_expect_tx(&full_bar[stage], pass ? 2 * kAlPlane : kAlPlane);
-                        tma_load_2d(sk, &tmap_kv, &full_bar[stage], p.C + h * 64, b * p.N_src + j * kAlKB);
-                        if (pass) tma_load_2d(sk + kAlPlane, &tmap_kv, &full_bar[stage], 2 * p.C + h * 64, b * p.N_src + j * kAlKB);
+                        tma_load_3d(sk, &tmap_kv, &full_bar[stage], p.C + h * 64, j * kAlKB, b);
+                        if (pass) tma_load_3d(sk + kAlPlane, &tmap_kv, &full_bar[stage], 2 * p.C + h * 64, j * kAlKB, b);
                         AL_TRACE(n, 1 + pass * 3 + (j < 3 ? j : 2));
                     }
                 }
@@ -468,15 +467,13 @@ attention_long_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     }
 }
 
-int make_tmap_bf16_2d_box(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems,
-                          int box_cols, int box_rows);      // gemm_tcgen05.cu
+int make_tmap_bf16_3d_ld(CUtensorMap* map, const void* base, long long batch, long long rows, long long cols, int box_rows);   // gemm_tcgen05.cu
 
 static int al_num_sms() {
-    static int n = 0;
+    static int n_dev[kMaxDevices] = {};          // per device: one process may drive several GPUs
+    int& n = n_dev[current_device()];
     if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, current_device());
         if (n <= 0) n = 148;
     }
     return n;
@@ -506,8 +503,8 @@ int launch_attention_long(const void* qkv, const int32_t* row_map, void* out, in
         attr_done = true;
     }
     CUtensorMap tq, tkv;
-    if (int rc = make_tmap_bf16_2d_box(&tq, qkv, (long long)B * N_src, 3LL * C, 3LL * C, 64, 128)) return rc;
-    if (int rc = make_tmap_bf16_2d_box(&tkv, qkv, (long long)B * N_src, 3LL * C, 3LL * C, 64, kAlKB)) return rc;
+    if (int rc = make_tmap_bf16_3d_ld(&tq, qkv, B, N_src, 3LL * C, 128)) return rc;           // per image: a box never reads the next image
+    if (int rc = make_tmap_bf16_3d_ld(&tkv, qkv, B, N_src, 3LL * C, kAlKB)) return rc;
     const int grid = p.n_items < al_num_sms() ? p.n_items : al_num_sms();
     cudaError_t le = launch_kernel(attention_long_kernel, dim3(grid), dim3(kAlThreads), (size_t)kAlSmem, stream, 1, tq, tkv, p);
     count_launch();

@@ -161,10 +161,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
                     for (int t = 0; t < nsub; ++t) {
                         const int item = unit_item(p, u, t);
                         const int b = item / p.H, h = item - b * p.H;
-                        // rows past the image's Np belong to the next image (finite values, masked by the softmax)
-                        // or lie past the tensor (zero-filled)
-                        tma_load_2d(sq + pl * p.plane_bytes + t * (128 * 128), &tmap_qkv, pl < 2 ? &qk_full[stage] : &v_full[stage],
-                                    pl * p.C + h * 64, b * p.N_src);
+                        // 3-d map [image][token][3C]: rows past the image's tokens are zero-filled, never the next image's
+                        tma_load_3d(sq + pl * p.plane_bytes + t * (128 * 128), &tmap_qkv, pl < 2 ? &qk_full[stage] : &v_full[stage],
+                                    pl * p.C + h * 64, 0, b);
                     }
                 AT_TRACE(n, 1);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -493,6 +492,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
 int make_tmap_bf16_2d_box(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems,
                           int box_cols, int box_rows);      // gemm_tcgen05.cu
 int make_tmap_bf16_3d_box(CUtensorMap* map, const void* base, long long batch, long long rows, long long cols, int box_rows);
+int make_tmap_bf16_3d_ld(CUtensorMap* map, const void* base, long long batch, long long rows, long long cols, int box_rows);
 
 static int at_num_sms() {
     static int n_dev[kMaxDevices] = {};          // per device: one process may drive several GPUs
@@ -532,7 +532,7 @@ int launch_attention_tc(const void* qkv, const int32_t* row_map, void* out, int 
     RAJNI_REQUIRE(p.stages >= 2, RAJNI_EINVAL, "attention_tc: Np=%d leaves room for %d stage(s)", Np, p.stages);
     const int smem = p.stages * 3 * p.plane_bytes + kAtOutStage + 256 + 1024;
     CUtensorMap tmap;
-    if (int rc = make_tmap_bf16_2d_box(&tmap, qkv, (long long)B * N_src, 3LL * C, 3LL * C, 64, p.Np_pad)) return rc;
+    if (int rc = make_tmap_bf16_3d_ld(&tmap, qkv, B, N_src, 3LL * C, p.Np_pad)) return rc;
     CUtensorMap tmap_out;
     RAJNI_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15u) == 0, RAJNI_EINVAL, "attention_tc: out must be 16-byte aligned (TMA store)");
     if (int rc = make_tmap_bf16_3d_box(&tmap_out, out, B, Np, C, 32)) return rc;

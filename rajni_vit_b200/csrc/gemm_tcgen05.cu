@@ -275,8 +275,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         rptr = p.residual + (p.res_row_map ? (long long)__ldg(p.res_row_map + m) : (long long)m) * p.ldres + ncol0;
 #pragma unroll
                         for (int c = 0; c < NCH; ++c) {
-                            ldg256_nc(rptr + c * 32, *reinterpret_cast<uint32_t(*)[8]>(&rr[c][0]));
-                            ldg256_nc(rptr + c * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rr[c][8]));
+                            ldg256(rptr + c * 32, *reinterpret_cast<uint32_t(*)[8]>(&rr[c][0]));      // (coherent: the residual may alias D)
+                            ldg256(rptr + c * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rr[c][8]));
                         }
                     }
                 }

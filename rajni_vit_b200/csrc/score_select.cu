@@ -42,9 +42,11 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
     return warp_sum(t);                    // every warp reduces the same 16 values
 }
 
-// order-preserving float -> uint key (larger float => larger key; +NaN sorts largest like topk)
+// order-preserving float -> uint key (larger float => larger key); any NaN, whatever its sign bit, gets the largest key:
+// torch.topk treats NaN as greater than every number (attention.py:35)
 __device__ __forceinline__ uint32_t float_key(float f) {
     uint32_t u = __float_as_uint(f + 0.0f);        // -0.0 -> +0.0: they compare equal in the reference
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 

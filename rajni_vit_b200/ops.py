@@ -102,18 +102,28 @@ SPLIT_SCORE_MAX_BATCH = 96      # below this many images per launch the K/V pass
 _score_ws = {}
 
 
+def score_workspace_bytes(B: int, N: int, C: int, num_heads: int) -> int:
+    """Scratch bytes the split score path needs (rajni_score_select_workspace_bytes)."""
+    return int(_lib.load().rajni_score_select_workspace_bytes(B, N, C, num_heads))
+
+
 def _score_workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
-    ws = _score_ws.get(dev)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-        _score_ws[dev] = ws
-    return ws
+    """Process-wide scratch for callers that do not bring their own (stand-alone ops.score_select calls).  Grow-only and
+    NEVER freed: a CUDA graph captured by some other caller may have baked an older buffer's address in, so superseded
+    buffers stay alive in the list.  RAJNIViTWrapper owns its scratch (``workspace=``) and does not come here."""
+    bufs = _score_ws.setdefault(dev, [])
+    if not bufs or bufs[-1].numel() < nbytes:
+        bufs.append(torch.empty(nbytes, device=dev, dtype=torch.uint8))
+    return bufs[-1]
 
 
 def score_select(qkv: torch.Tensor, num_heads: int, keep: int, eps: float = 1e-6, want_scores: bool = False,
-                 keep_idx=None, next_scores=None, row_map=None, scores=None, split: Optional[bool] = None):
+                 keep_idx=None, next_scores=None, row_map=None, scores=None, split: Optional[bool] = None,
+                 workspace: Optional[torch.Tensor] = None):
     """Fused importance + selection on qkv [B,N,3C] bf16.
-    Returns (scores or None, keep_idx, next_scores, row_map)."""
+    Returns (scores or None, keep_idx, next_scores, row_map).
+    ``workspace``: uint8 scratch of at least ``score_workspace_bytes(B, N, C, H)`` for the split path (small batches); a
+    caller that replays CUDA graphs must pass one it owns, so that the captured address lives as long as the graph."""
     _bf16c(qkv)
     B, N, C3 = qkv.shape
     dev = qkv.device
@@ -130,7 +140,9 @@ def score_select(qkv: torch.Tensor, num_heads: int, keep: int, eps: float = 1e-6
     work = B * (2 * N * C * 2 + C * 2 + 8 * (keep + 1))
     if split:
         nbytes = int(lib.rajni_score_select_workspace_bytes(B, N, C, num_heads))
-        ws = _score_workspace(dev, nbytes)
+        ws = workspace if workspace is not None else _score_workspace(dev, nbytes)
+        if ws.numel() * ws.element_size() < nbytes or ws.device != dev:
+            raise ValueError(f"score_select: workspace of {ws.numel() * ws.element_size()} B on {ws.device}, need {nbytes} B on {dev}")
         _call("score_select", work, lib.rajni_score_select_split, qkv.data_ptr(), B, N, C, num_heads, keep, eps, _ptr(scores),
               keep_idx.data_ptr(), next_scores.data_ptr(), row_map.data_ptr(), ws.data_ptr(), ws.numel(), _stream(qkv))
     else:
@@ -201,9 +213,10 @@ LONG_SEQ = 256          # above this many kept tokens the key-block kernel runs;
 
 def attention(qkv: torch.Tensor, row_map: Optional[torch.Tensor], B: int, N_src: int, Np: int, C: int,
               num_heads: int, scale: float, out: Optional[torch.Tensor] = None, reverse: bool = False,
-              compact: Optional[torch.Tensor] = None) -> torch.Tensor:
+              compact: Optional[torch.Tensor] = None, impl: int = _lib.ATTN_AUTO) -> torch.Tensor:
     """Attention over the Np kept tokens of each image.  -> [B*Np, C] bf16
 
+    ``impl``: _lib.ATTN_AUTO (default) or a specific kernel (tests / A-B timing), see include/rajni_b200.h.
     Np <= 256: the kept-token gather is fused into the kernel's loads (cp.async by row index).
     Np  > 256: the key-block kernel streams K/V blocks with TMA, which needs consecutive rows, so the kept rows are
     compacted once with ``gather_rows`` (HBM-bound, into ``compact`` [B*Np, 3C] if given) and the dense path runs on them:
@@ -212,8 +225,8 @@ def attention(qkv: torch.Tensor, row_map: Optional[torch.Tensor], B: int, N_src:
     if row_map is not None and Np > LONG_SEQ:
         qkv = gather_rows(qkv.view(-1, 3 * C), row_map, out=None if compact is None else compact[: B * Np])
         row_map, N_src = None, Np
-    _call("attention", 4.0 * B * Np * Np * C, _lib.load().rajni_attention_fwd,
-          qkv.data_ptr(), _ptr(row_map), out.data_ptr(), B, N_src, Np, C, num_heads, scale, int(reverse), _stream(qkv))
+    _call("attention", 4.0 * B * Np * Np * C, _lib.load().rajni_attention_fwd_ex,
+          qkv.data_ptr(), _ptr(row_map), out.data_ptr(), B, N_src, Np, C, num_heads, scale, int(reverse), int(impl), _stream(qkv))
     return out
 
 

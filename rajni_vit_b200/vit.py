@@ -160,3 +160,33 @@ def create_model(name: str, seed: int | None = 0, bf16_round: bool = True,
             for p in model.parameters():
                 p.copy_(p.to(torch.bfloat16).to(torch.float32))
     return model.eval()
+
+
+def randomize_trained_like(model: VisionTransformer, seed: int = 0, outlier_channels: int = 4, outlier_scale: float = 20.0,
+                           bf16_round: bool = True) -> VisionTransformer:
+    """Give a random-init stand-in the parameter STATISTICS of a trained ViT (no pretrained weights exist offline):
+    LayerNorm gains spread over [0.3, 2.5] and non-zero shifts, biases of O(0.5), and a few "massive activation"
+    channels - residual-stream channels that every block's fc2 / proj pushes far from zero, with the matching large
+    LayerNorm gains trained models show there.  Exercises the folded-LayerNorm path (W*gamma, b + W beta, E[x^2]-mean^2
+    statistics at large |mean|/sigma) that gamma = 1, beta = 0 never touches."""
+    g = torch.Generator().manual_seed(seed)
+    C = model.embed_dim
+    hot = torch.randperm(C, generator=g)[:outlier_channels]
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("norm1.weight") or name.endswith("norm2.weight") or name == "norm.weight":
+                p.copy_(0.3 + 2.2 * torch.rand(p.shape, generator=g))
+            elif name.endswith("norm1.bias") or name.endswith("norm2.bias") or name == "norm.bias":
+                p.copy_(0.3 * torch.randn(p.shape, generator=g))
+            elif name.endswith(".bias"):
+                p.copy_(0.5 * torch.randn(p.shape, generator=g))
+        for blk in model.blocks:
+            blk.mlp.fc2.bias[hot] += outlier_scale * (0.5 + torch.rand(outlier_channels, generator=g))
+            blk.attn.proj.bias[hot] -= 0.25 * outlier_scale * torch.rand(outlier_channels, generator=g)
+            for nrm in (blk.norm1, blk.norm2):
+                nrm.weight[hot] *= 0.1                      # trained models damp their massive channels at the next norm
+        model.pos_embed[..., hot] += outlier_scale
+        if bf16_round:
+            for p in model.parameters():
+                p.copy_(p.to(torch.bfloat16).to(torch.float32))
+    return model

@@ -67,6 +67,7 @@ class RAJNIViTWrapper(nn.Module):
         self._packs = PackCache()
         self._ws = {}
         self._graphs = {}
+        self._param_list = None
         # None = automatic: replay a captured CUDA graph when the batch is small enough to be launch-bound
         env = os.environ.get("RAJNI_CUDA_GRAPH", "")
         self.use_cuda_graph: Optional[bool] = None if env == "" else env != "0"
@@ -123,10 +124,12 @@ class RAJNIViTWrapper(nn.Module):
         self._packs.clear()
         self._ws.clear()
         self._graphs = {}
+        self._param_list = None
         return super()._apply(fn, *a, **kw)
 
     def load_state_dict(self, *a, **kw):
         self._graphs = {}
+        self._param_list = None
         return super().load_state_dict(*a, **kw)
 
     def get_last_stats(self):
@@ -162,6 +165,9 @@ class RAJNIViTWrapper(nn.Module):
             stat_slots=ops.row_stats_slots(C),
             stats=torch.zeros((ops.row_stats_slots(C), B * N0, 2), device=dev, dtype=torch.float32),
             sel={},
+            # scratch of the split score path (small batches): owned here, so a captured graph's pointer lives with the graph
+            score_ws=(torch.empty(max(ops.score_workspace_bytes(B, N0, C, blk.attn.num_heads) for blk in self.blocks),
+                                  device=dev, dtype=torch.uint8) if B <= ops.SPLIT_SCORE_MAX_BATCH else None),
         )
         self._ws = {key: ws}        # keep one shape resident
         self._graphs = {}           # a captured graph points into the workspace it was captured with
@@ -184,8 +190,14 @@ class RAJNIViTWrapper(nn.Module):
             use = x.shape[0] * ((x.shape[2] // 16) * (x.shape[3] // 16) + 1) <= AUTO_GRAPH_MAX_ROWS
         if not use or x.device.type != "cuda" or x.dim() != 4 or ops._prof is not None:      # (the per-kernel profiler times eager launches)
             return self._forward_eager(x)
-        key = (tuple(x.shape), x.dtype, x.device, self.training)
-        wsig = tuple((q.data_ptr(), q._version) for q in self.parameters())
+        # what _forward_eager reads besides the input: the schedule of the pruned blocks (attention.py:25-32) ...
+        sched = tuple((blk.attn.keep_ratio, blk.attn.update) if blk.has_pruner else None for blk in self.blocks)
+        key = (tuple(x.shape), x.dtype, x.device, self.training, sched, self.input_norm)
+        # ... and the parameters.  Storage changes go through _apply / load_state_dict (which drop the graphs); in-place
+        # updates bump the tensors' version counters, summed here over a parameter list that is built once.
+        if self._param_list is None:
+            self._param_list = list(self.parameters())
+        wsig = sum(q._version for q in self._param_list)
         entry = self._graphs.get(key)
         if entry is None or entry[5] != wsig:
             x_static = x.clone()
@@ -209,6 +221,9 @@ class RAJNIViTWrapper(nn.Module):
             raise ValueError(f"expected images [B,3,S,S] with S a multiple of 16, got {tuple(x.shape)}")
         if x.device.type != "cuda":
             raise RuntimeError("RAJNIViTWrapper (B200) runs on CUDA tensors only; there is no CPU path")
+        if self.m.pos_embed.device != x.device or self.m.head.weight.device != x.device:
+            raise RuntimeError(f"Expected all tensors to be on the same device: input on {x.device}, model on "
+                               f"{self.m.pos_embed.device} (call .to(device) on the wrapper first)")
         if self.training:
             for blk in self.blocks:
                 for d in (blk.attn.proj_drop, getattr(blk.mlp, "drop1", None), getattr(blk.mlp, "drop2", None)):
@@ -278,7 +293,7 @@ class RAJNIViTWrapper(nn.Module):
                 keep_idx, next_scores, row_map = sel
                 if attn.update or scores is None:                                     # attention.py:25-28
                     ops.score_select(ws["qkv"][: B * N].view(B, N, 3 * C), H, keep,
-                                     keep_idx=keep_idx, next_scores=next_scores, row_map=row_map)
+                                     keep_idx=keep_idx, next_scores=next_scores, row_map=row_map, workspace=ws["score_ws"])
                 else:
                     ops.select(scores, keep, keep_idx=keep_idx, next_scores=next_scores, row_map=row_map)
                 if Np > ops.LONG_SEQ and "qkvc" not in ws:                             # compaction buffer, long sequences only

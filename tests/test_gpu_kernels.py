@@ -253,6 +253,43 @@ def test_gemm_layernorm_folded(ops, M, C, N, gelu):
     assert not bad.any(), f"{int(bad.sum())} of {bad.numel()} elements out of tolerance; first at {bad.nonzero()[0].tolist()}"
 
 
+@pytest.mark.parametrize("ratio", [0.0, 10.0, 50.0, 100.0])
+def test_layernorm_fold_statistics_at_large_mean(ops, ratio):
+    """The folded LayerNorm takes the variance as E[x^2] - mean^2 from fp32 partial sums (gemm_tcgen05.cu epilogue).
+    Rows whose mean is `ratio` standard deviations from zero (massive-activation rows of trained ViTs sit near 10-30)
+    must still normalise correctly: reference = fp64 LayerNorm -> Linear on the same bf16 x."""
+    M, C, N = 256, 768, 256
+    g = torch.Generator().manual_seed(int(ratio) + 5)
+    sigma = 0.5 + torch.rand(M, 1, generator=g)
+    x = bf16_round(ratio * sigma * torch.sign(torch.randn(M, 1, generator=g)) + sigma * torch.randn(M, C, generator=g))
+    eye = torch.eye(C)
+    slots = ops.row_stats_slots(C)
+    stats = torch.zeros((slots, M, 2), device="cuda")
+    zero = torch.zeros(M, C)
+    xd = ops.gemm(dev(x, torch.bfloat16), dev(eye, torch.bfloat16), dev(torch.zeros(C)), M, C, C,
+                  residual=dev(zero, torch.bfloat16), ldres=C, row_stats=stats)          # stores x itself + its row sums
+    assert torch.equal(xd.float().cpu(), x)
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g) * 0.2
+    w = bf16_round(torch.randn(N, C, generator=g) / math.sqrt(C))
+    bias = torch.randn(N, generator=g)
+    wg = bf16_round(w * gamma[None, :])
+    xs = x.double()
+    mean, var = xs.mean(1, keepdim=True), xs.var(1, unbiased=False, keepdim=True)
+    ref = ((xs - mean) / torch.sqrt(var + 1e-6) * gamma.double() + beta.double()) @ (wg.double() / gamma.double()[None, :]).t() + bias.double()
+    out = ops.gemm(xd, dev(wg, torch.bfloat16), dev(bias + (wg / gamma[None, :]) @ beta), M, N, C,
+                   ln=(stats, slots, dev(wg.sum(dim=1)), 1e-6)).float().cpu().double()
+    # rstd as the kernel's statistics give it, against the exact one
+    tot = stats.sum(dim=0).double().cpu()
+    m_k = tot[:, 0] / C
+    v_k = (tot[:, 1] / C - m_k * m_k).clamp_min(0)
+    rstd_err = ((1 / torch.sqrt(v_k + 1e-6)) / (1 / torch.sqrt(var[:, 0] + 1e-6)) - 1).abs().max().item()
+    err = (out - ref).abs()
+    print(f"[ln stats] |mean|/sigma = {ratio:5.1f}: rstd relative error {rstd_err:.2e}, max |dout| {err.max().item():.3e} (ref rms {ref.pow(2).mean().sqrt().item():.2f})")
+    assert rstd_err < 5e-3
+    assert (err <= BF16_RTOL * ref.abs() + 4e-3 + 4 * rstd_err * ref.abs()).all()
+
+
 def test_gelu_matches_erf(ops):
     """The epilogue's GELU is a polynomial form of x*Phi(x); check it against erf over the whole useful range.
     acc = 0 (zero weights), so out[m, n] = gelu(bias[n]) exactly as the epilogue sees fp32 inputs."""
@@ -279,11 +316,26 @@ def test_gelu_matches_erf(ops):
         assert ((got - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-6).all()
 
 
+def test_select_nan_sorts_largest(ops):
+    """torch.topk treats NaN (either sign bit) as larger than every number: NaN-scored tokens are kept first."""
+    s = make_scores(2, 33, 5)
+    s[0, 7] = float("nan")
+    s[1, 20] = -float("nan")
+    keep = 5
+    idx, _, _ = ops.select(dev(s), keep)
+    assert 7 in idx[0].tolist() and 20 in idx[1].tolist()
+    ref = torch.topk(s[:, 1:], keep, dim=1).indices + 1
+    for b in range(2):
+        assert set(idx[b, 1:].tolist()) == set(ref[b].tolist())
+
+
 # ------------------------------------------------------------------ attention
 @pytest.mark.parametrize("B,N,Np,H", [(2, 17, 17, 2), (3, 197, 197, 3), (2, 197, 173, 12), (2, 173, 152, 12),
                                       (2, 152, 121, 12), (2, 121, 87, 12), (1, 577, 507, 12), (2, 577, 577, 3), (1, 507, 446, 12), (3, 357, 257, 6), (2, 300, 300, 2), (1, 1000, 700, 2), (2, 64, 64, 1),
                                       (2, 65, 65, 1), (2, 197, 2, 3), (2, 250, 250, 2), (1, 300, 240, 3), (2, 256, 256, 1), (3, 130, 129, 2), (2, 192, 192, 2), (2, 200, 193, 2)])
 def test_attention(ops, B, N, Np, H):
+    """Every kernel that covers the shape (include/rajni_b200.h: RAJNI_ATTN_*), not only the one the dispatcher picks."""
+    from rajni_vit_b200 import _lib
     C = H * 64
     qkv = make_qkv(B, N, H, 64, 500 + N + Np)
     g = torch.Generator().manual_seed(N * Np)
@@ -296,10 +348,36 @@ def test_attention(ops, B, N, Np, H):
     else:
         rmap, kept = None, qkv
     ref = orc.mha(kept.double(), H, 0.125).reshape(B * Np, C)
-    got = ops.attention(dev(qkv, torch.bfloat16).view(B * N, 3 * C), None if rmap is None else dev(rmap),
-                        B, N, Np, C, H, 0.125).cpu().double()
-    report(f"attn N={N} Np={Np}", got, ref)
-    assert ((got - ref).abs() <= 2 * BF16_RTOL * ref.abs() + 4e-3).all()
+    impls = [("auto", _lib.ATTN_AUTO)]
+    if (Np + 15) // 16 * 16 <= 224:
+        impls.append(("pipe", _lib.ATTN_PIPE))
+    if Np <= 256:
+        impls.append(("tc", _lib.ATTN_TC))
+    for name, impl in impls:
+        for reverse in (False, True):
+            got = ops.attention(dev(qkv, torch.bfloat16).view(B * N, 3 * C), None if rmap is None else dev(rmap),
+                                B, N, Np, C, H, 0.125, impl=impl, reverse=reverse).cpu().double()
+            report(f"attn[{name}{',rev' if reverse else ''}] N={N} Np={Np}", got, ref)
+            assert ((got - ref).abs() <= 2 * BF16_RTOL * ref.abs() + 4e-3).all(), name
+
+
+@pytest.mark.parametrize("N", [197, 130, 87, 300])
+def test_attention_images_are_isolated(ops, N):
+    """A NaN/Inf in one image must not reach another image's output (dense calls load per-image, zero-filled boxes)."""
+    from rajni_vit_b200 import _lib
+    B, H = 3, 2
+    C = H * 64
+    qkv = make_qkv(B, N, H, 64, 77 + N)
+    clean = dev(qkv, torch.bfloat16).view(B * N, 3 * C)
+    dirty = qkv.clone()
+    dirty[1] = float("nan")
+    dirty = dev(dirty, torch.bfloat16).view(B * N, 3 * C)
+    impls = [_lib.ATTN_AUTO] + ([_lib.ATTN_PIPE, _lib.ATTN_TC] if N <= 224 else [])
+    for impl in impls:
+        a = ops.attention(clean, None, B, N, N, C, H, 0.125, impl=impl).view(B, N, C)
+        b = ops.attention(dirty, None, B, N, N, C, H, 0.125, impl=impl).view(B, N, C)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]), impl
+        assert torch.isfinite(a).all()
 
 
 # ------------------------------------------------------------------ patch embed

@@ -3,6 +3,7 @@ data-parallel path of evaluate_model under a world_size-2 gloo group.
 
 No compute entry point of librajni_b200.so is called here - there is no CPU path to call.
 """
+import copy
 import ctypes
 import json
 import os
@@ -179,3 +180,58 @@ def test_standin_state_dict_uses_timm_names():
                      "blocks.0.attn.proj.weight": (192, 192), "blocks.11.mlp.fc1.weight": (768, 192),
                      "blocks.11.mlp.fc2.bias": (192,), "norm.weight": (192,), "head.weight": (1000, 192)}.items():
         assert tuple(sd[k].shape) == shape, k
+
+
+# ------------------------------------------------------------------ real-weights path (run.py:89-92,126-129)
+def _ckpt_model():
+    from rajni_vit_b200.vit import create_model, randomize_trained_like
+    return randomize_trained_like(create_model("vit_micro_patch16_64", seed=3), seed=4)
+
+
+@pytest.mark.parametrize("fmt", ["pt", "safetensors"])
+@pytest.mark.parametrize("family", ["timm", "wrapper", "dataparallel"])
+def test_load_checkpoint_key_families(tmp_path, fmt, family):
+    """timm keys, a saved wrapper's duplicated m.blocks.* / blocks.* families, and a module.-prefixed copy all load to
+    the same model; the architecture is inferred from the shapes."""
+    import rajni_vit_b200 as pkg
+    from rajni_vit_b200.checkpoint import write_safetensors
+    src = _ckpt_model()
+    if family == "timm":
+        sd = src.state_dict()
+    elif family == "wrapper":
+        sd = pkg.RAJNIViTWrapper(copy.deepcopy(src), {1: {"keep_ratio": 0.7}}).state_dict()
+        assert any(k.startswith("m.blocks.") for k in sd) and any(k.startswith("blocks.") for k in sd)
+    else:
+        sd = {"state_dict": {"module." + k: v for k, v in src.state_dict().items()}}
+    path = str(tmp_path / f"w.{fmt}")
+    if fmt == "pt":
+        torch.save(sd, path)
+    else:
+        write_safetensors(path, sd["state_dict"] if "state_dict" in sd else sd)
+    got = pkg.load_checkpoint(path)
+    assert (got.embed_dim, len(got.blocks), got.blocks[0].attn.num_heads, got.num_classes) == (128, 4, 2, 1000)
+    assert got.patch_embed.img_size == (64, 64)
+    for (k, a), (_, b) in zip(src.state_dict().items(), got.state_dict().items()):
+        assert torch.equal(a, b), k
+    # loading into an existing wrapper updates its base model in place
+    wrap = pkg.RAJNIViTWrapper(_ckpt_model(), {1: {"keep_ratio": 0.7}})
+    with torch.no_grad():
+        wrap.m.head.weight.zero_()
+    pkg.load_checkpoint(path, model=wrap)
+    assert torch.equal(wrap.m.head.weight, src.head.weight)
+
+
+def test_load_checkpoint_rejects_what_the_wrapper_cannot_run(tmp_path):
+    import rajni_vit_b200 as pkg
+    sd = _ckpt_model().state_dict()
+    with pytest.raises(NotImplementedError, match="ls1"):
+        pkg.load_checkpoint({**sd, "blocks.0.ls1.gamma": torch.ones(128)})
+    with pytest.raises(KeyError):
+        pkg.load_checkpoint({k: v for k, v in sd.items() if k != "blocks.2.mlp.fc1.weight"})
+    with pytest.raises(KeyError, match="unexpected"):
+        pkg.load_checkpoint({**sd, "blocks.0.attn.extra": torch.ones(1)})
+    clash = {**sd, "m.head.bias": sd["head.bias"] + 1}
+    with pytest.raises(ValueError, match="two different tensors"):
+        pkg.load_checkpoint(clash)
+    with pytest.raises(KeyError, match="not a timm-named"):
+        pkg.load_checkpoint({"encoder.layer.0.weight": torch.ones(2)})
