@@ -57,6 +57,7 @@ struct AttnTcParams {
     int N_src, Np, Np_pad, C, H, BH, two_tiles, n_units;
     int o_col, o_outside;       // TMEM column of O inside a tile; o_outside = O does not overlap S's columns
     int split_col;              // > 0 (needs o_outside): P V starts once P's columns [0, split_col) are written, the rest follows
+    int ksplit;                 // key column where attention_pipe.cu splits a row between its two exp warps (row-sum order)
     int plane_bytes, stages;    // bytes of one Q/K/V plane of a stage (1024-aligned); pipeline depth
     int reverse;                // walk the (image, head) items last-to-first (L2 reuse hint)
     float scale_log2;
@@ -378,40 +379,46 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
                 if ((tid & 127) == 0) AT_TRACE(n, 13 + 8 * t);
                 // ---- pass 2: p = exp2((s - max) * scale * log2 e), row sum, bf16 P back into TMEM.
                 // P chunk c lands on columns [16c, 16c+16): always behind the S columns still to be read.
+                // The row sum is taken in the order attention_pipe.cu takes it - even and odd columns of the key halves
+                // [0, ksplit) and [ksplit, Np_pad) separately, (A0 + A1) + (B0 + B1) - so that the two kernels agree bit for
+                // bit and a keep_ratio of 1.0 (gathered call) reproduces the un-pruned block (dense call) exactly.
                 const float mb = mx * sl2;
-                sum = 0.f;
+                const int ksplit = p.ksplit;
+                float sa0 = 0.f, sa1 = 0.f, sb0 = 0.f, sb1 = 0.f;
+                auto add16 = [&](const float (&e)[32], int off, bool in_a) {
+                    if (in_a) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) { sa0 += e[off + j]; sa1 += e[off + j + 1]; }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) { sb0 += e[off + j]; sb1 += e[off + j + 1]; }
+                    }
+                };
                 auto exp_step = [&](const uint32_t (&cur)[32], uint32_t (&nxt)[32], int c0) {
                     tmem_ld_wait();
                     if (c0 + 32 < Np_pad) tmem_ld32(trow + c0 + 32, nxt);      // may run <= 16 columns past Np_pad: still this tile's
+                    float e[32];
                     if (Np_pad - c0 >= 32) {
                         uint32_t pk[16];
                         if (c0 + 32 <= Np) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 2) {
-                                const float e0 = ex2_approx(fmaf(__uint_as_float(cur[j]), sl2, -mb));
-                                const float e1 = ex2_approx(fmaf(__uint_as_float(cur[j + 1]), sl2, -mb));
-                                sum += e0 + e1;
-                                pk[j >> 1] = float2_to_bf16x2(e0, e1);
-                            }
+                            for (int j = 0; j < 32; ++j) e[j] = ex2_approx(fmaf(__uint_as_float(cur[j]), sl2, -mb));
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 2) {
-                                const float e0 = (c0 + j < Np) ? ex2_approx(fmaf(__uint_as_float(cur[j]), sl2, -mb)) : 0.f;
-                                const float e1 = (c0 + j + 1 < Np) ? ex2_approx(fmaf(__uint_as_float(cur[j + 1]), sl2, -mb)) : 0.f;
-                                sum += e0 + e1;
-                                pk[j >> 1] = float2_to_bf16x2(e0, e1);
-                            }
+                            for (int j = 0; j < 32; ++j) e[j] = (c0 + j < Np) ? ex2_approx(fmaf(__uint_as_float(cur[j]), sl2, -mb)) : 0.f;
                         }
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) pk[j >> 1] = float2_to_bf16x2(e[j], e[j + 1]);
+                        add16(e, 0, c0 < ksplit);
+                        add16(e, 16, c0 + 16 < ksplit);
                         tmem_st16(trow + (c0 >> 1), pk);
                     } else {                                                   // 16-column tail
                         uint32_t pk[8];
 #pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            const float e0 = (c0 + j < Np) ? ex2_approx(fmaf(__uint_as_float(cur[j]), sl2, -mb)) : 0.f;
-                            const float e1 = (c0 + j + 1 < Np) ? ex2_approx(fmaf(__uint_as_float(cur[j + 1]), sl2, -mb)) : 0.f;
-                            sum += e0 + e1;
-                            pk[j >> 1] = float2_to_bf16x2(e0, e1);
-                        }
+                        for (int j = 0; j < 16; ++j) e[j] = (c0 + j < Np) ? ex2_approx(fmaf(__uint_as_float(cur[j]), sl2, -mb)) : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) pk[j >> 1] = float2_to_bf16x2(e[j], e[j + 1]);
+                        add16(e, 0, c0 < ksplit);
                         tmem_st8(trow + (c0 >> 1), pk);
                     }
                 };
@@ -430,6 +437,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
                     if (c0 + 64 == split) half_ready();
                 }
                 tmem_st_wait();
+                sum = (sa0 + sa1) + (sb0 + sb1);
             } else if (p.split_col) {
                 mbar_arrive(&p_half[t]);
             }
@@ -519,6 +527,7 @@ int launch_attention_tc(const void* qkv, const int32_t* row_map, void* out, int 
     p.two_tiles = Np > 128;
     p.n_units = p.two_tiles ? p.BH : (p.BH + 1) / 2;
     p.scale_log2 = scale * 1.4426950408889634f;
+    p.ksplit = ((p.Np_pad / 2) + 15) & ~15;
     p.o_outside = p.Np_pad <= 192;
     p.o_col = p.o_outside ? 192 : 128;
     static const bool nosplit = getenv("RAJNI_ATTN_NOSPLIT") != nullptr;      // A/B switch

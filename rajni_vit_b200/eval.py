@@ -13,6 +13,9 @@ Differences, all deliberate:
     sharded contiguously across ranks (images are independent); the
     only collective is one all-reduce of (correct, total, images) and one MAX of
     the elapsed time at the very end, so throughput = all images / slowest rank.
+    A foreign loader is sharded by slicing each batch after loading; a loader from
+    ``rajni_vit_b200.data.sharded_loader`` (``rajni_sharded = True``) already yields
+    this rank's shard - 1/N of the decode work - and is used as it comes.
 """
 from __future__ import annotations
 
@@ -55,8 +58,10 @@ def evaluate_model(model, dataloader, device="cuda", max_batches=None, warmup=5,
     model.eval()
     model.to(device)
 
+    presharded = bool(getattr(dataloader, "rajni_sharded", False))      # data.sharded_loader: batches are this rank's already
+
     def take(t):
-        if world == 1:
+        if world == 1 or presharded:
             return t
         lo, hi = shard_bounds(t.shape[0], rank, world)
         return t[lo:hi]

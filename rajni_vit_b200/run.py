@@ -12,6 +12,8 @@ Differences from the reference CLI, all deliberate:
   * ``--synthetic N`` replaces the ImageFolder pipeline by N seeded random batches (no dataset, no labels that mean
     anything: accuracy is only a consistency check then);
   * ``--uint8_input`` ships uint8 crops and normalises inside the patch kernel (extension; same logits, 4x fewer H2D bytes);
+  * ``--ckpt file`` loads timm-named weights from a .safetensors / .pt file (no hub access needed);
+  * under torchrun every rank decodes only its shard of each batch (``data.sharded_loader``);
   * without ``timm`` (not installable here) the stand-in ViT with random weights is used and the fact is printed.
 """
 from __future__ import annotations
@@ -39,6 +41,8 @@ def get_args(argv=None):
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--max_batches", type=int, default=None)
     ap.add_argument("--compare_base", action="store_true", help="also evaluate the un-pruned model")
+    ap.add_argument("--ckpt", type=str, default=None,
+                    help="timm-named ViT weights (.safetensors / .pt) to load instead of timm's hub (rajni_vit_b200.load_checkpoint)")
     ap.add_argument("--uint8_input", action="store_true",
                     help="ship uint8 crops to the GPU and normalise inside the patch kernel (4x fewer H2D bytes; same logits)")
     args = ap.parse_args(argv)
@@ -47,8 +51,12 @@ def get_args(argv=None):
     return args
 
 
-def build_model(name: str):
-    """timm's pretrained model when timm is present, otherwise the random-init stand-in with timm's attribute names."""
+def build_model(name: str, ckpt: str = None):
+    """A checkpoint file when given (architecture inferred from its shapes), else timm's pretrained model when timm is
+    present, otherwise the random-init stand-in with timm's attribute names."""
+    if ckpt:
+        from .checkpoint import load_checkpoint
+        return load_checkpoint(ckpt), f"weights from {ckpt}"
     try:
         import timm                                             # noqa: F401
         return timm.create_model(name, pretrained=True), "timm (pretrained)"
@@ -60,7 +68,7 @@ def build_model(name: str):
 IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)      # run.py:68
 
 
-def build_loader(args, image_size: int):
+def build_loader(args, image_size: int, rank: int = 0, world: int = 1):
     if args.synthetic > 0:
         g = torch.Generator().manual_seed(1234)
         shape = (args.batch_size, 3, image_size, image_size)
@@ -71,6 +79,9 @@ def build_loader(args, image_size: int):
     tail = [T.PILToTensor()] if args.uint8_input else [T.ToTensor(), T.Normalize(mean=IMAGENET_MEAN, std=IMAGENET_STD)]
     tf = T.Compose([T.Resize(int(image_size * 256 / 224), interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(image_size), *tail])
     ds = datasets.ImageFolder(args.data_path, tf)
+    if world > 1:          # every rank decodes only its shard of each global batch (data.py); same images per rank as slicing
+        from .data import sharded_loader
+        return sharded_loader(ds, args.batch_size, rank, world, num_workers=args.num_workers, pin_memory=args.pin_mem)
     return torch.utils.data.DataLoader(ds, batch_size=args.batch_size, shuffle=False, num_workers=args.num_workers,
                                        pin_memory=args.pin_mem, drop_last=False)
 
@@ -91,15 +102,15 @@ def main(argv=None):
     with open(args.schedule) as f:
         schedule = json.load(f)
 
-    base, origin = build_model(args.model)
+    base, origin = build_model(args.model, args.ckpt)
     say(f"model {args.model}: {origin}")
     size = getattr(getattr(base, "patch_embed", None), "img_size", (224, 224))
     size = size[0] if isinstance(size, (tuple, list)) else int(size)
-    loader = build_loader(args, size)
+    loader = build_loader(args, size, rank, world)
 
     results = {}
     if args.compare_base:
-        dense, _ = build_model(args.model)
+        dense, _ = build_model(args.model, args.ckpt)
         dense = RAJNIViTWrapper(dense, {})                       # no block pruned: the same kernels, all tokens
         if args.uint8_input:
             dense.set_input_normalization(IMAGENET_MEAN, IMAGENET_STD)

@@ -134,15 +134,35 @@ def _make_data():
     return [(torch.randn(7, 3, 8, 8, generator=g), torch.randint(0, 10, (7,), generator=g)) for _ in range(3)]
 
 
+class _DecodeCounting(torch.utils.data.Dataset):
+    """21 images in dataset form; counts how many this process "decoded"."""
+
+    def __init__(self):
+        self.batches, self.decoded = _make_data(), 0
+
+    def __len__(self):
+        return 21
+
+    def __getitem__(self, i):
+        self.decoded += 1
+        x, y = self.batches[i // 7]
+        return x[i % 7], y[i % 7]
+
+
 def _dp_worker(rank, world, port, out_path):
     import torch.distributed as dist
+    from rajni_vit_b200.data import sharded_loader
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         acc, ips = evaluate_model(_StubModel(), _make_data(), device="cpu", warmup=1, progress=False)
+        ds = _DecodeCounting()
+        acc2, _ = evaluate_model(_StubModel(), sharded_loader(ds, 7, rank, world), device="cpu", warmup=0, progress=False)
+        decoded = torch.tensor([ds.decoded])
+        dist.all_reduce(decoded)
         if rank == 0:
-            json.dump({"acc": acc, "ips": ips}, open(out_path, "w"))
+            json.dump({"acc": acc, "ips": ips, "acc_sharded_loader": acc2, "decoded_all_ranks": int(decoded)}, open(out_path, "w"))
     finally:
         dist.destroy_process_group()
 
@@ -159,6 +179,26 @@ def test_evaluate_model_data_parallel_gloo(tmp_path):
     got = json.load(open(out))
     assert got["acc"] == pytest.approx(acc1, abs=1e-9)
     assert got["ips"] > 0
+    # the rank-sharded loader gives the same answer with every image decoded exactly once across the ranks
+    assert got["acc_sharded_loader"] == pytest.approx(acc1, abs=1e-9)
+    assert got["decoded_all_ranks"] == 21
+
+
+def test_rank_sharded_batch_sampler_matches_slicing():
+    """For every global batch the ranks' shards are exactly the slices evaluate_model would cut (same images, same order)."""
+    from rajni_vit_b200.data import RankShardedBatchSampler
+    from rajni_vit_b200.eval import shard_bounds
+    for n, bs, world in ((21, 7, 2), (100, 32, 8), (10, 4, 3), (5, 8, 4), (64, 16, 1)):
+        per_rank = [list(RankShardedBatchSampler(n, bs, r, world)) for r in range(world)]
+        assert sorted(i for shards in per_rank for b in shards for i in b) == list(range(n))
+        for start in range(0, n, bs):
+            size = min(bs, n - start)
+            for r in range(world):
+                lo, hi = shard_bounds(size, r, world)
+                want = list(range(start + lo, start + hi))
+                if want:
+                    assert want in per_rank[r]
+        assert [len(RankShardedBatchSampler(n, bs, r, world)) for r in range(world)] == [len(p) for p in per_rank]
 
 
 def test_cli_flags_match_reference():
