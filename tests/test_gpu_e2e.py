@@ -366,7 +366,9 @@ def test_trained_like_checkpoint_end_to_end(pkg, tmp_path, name, sched, batch, s
     """A checkpoint whose parameters have a trained ViT's statistics (LayerNorm gains 0.3..2.5 and non-zero shifts,
     O(0.5) biases, a few massive-activation channels) goes file -> load_checkpoint -> wrapper -> logits; the oracle
     runs the same fp32 weights with our kept indices forced.  Logits: max |d| <= 3 % of the logit std + 0.02 (bf16
-    activations; the random-init models sit at 0.08 for std 0.57); kept sets exact outside the 3 % tie band."""
+    activations; the random-init models sit at 0.08 for std 0.57); kept sets exact outside a 6 % tie band (the residual
+    stream reaches +-250 here and the attention logits are ~3x those of a random-init model, so the bf16 rounding of q.k
+    moves the scores ~3x more than in test_forward_vs_oracle_full_models, whose band is 3 %)."""
     from rajni_vit_b200.checkpoint import write_safetensors
     from rajni_vit_b200.vit import create_model, randomize_trained_like
     base = randomize_trained_like(create_model(name, seed=0), seed=1)
@@ -393,6 +395,6 @@ def test_trained_like_checkpoint_end_to_end(pkg, tmp_path, name, sched, batch, s
     for rec, kidx in zip(trace, ours):
         if kidx is None:
             continue
-        ov, worst = near_tie_mismatch(kidx, rec["scores"], kidx.shape[1] - 1, 0.03)
+        ov, worst = near_tie_mismatch(kidx, rec["scores"], kidx.shape[1] - 1, 0.06)
         print(f"  block {rec['block']}: kept-set overlap {ov:.4f}, worst disagreeing token {worst:.2e} from the cut")
-        assert worst < 0.03
+        assert worst < 0.06 and ov > 0.98
