@@ -47,6 +47,7 @@ constexpr int kApBarBytes = 256;
 constexpr int kApSmemBudget = 227 * 1024 - 1024 - kApOutStage - kApAuxBytes - kApBarBytes;
 
 #ifdef RAJNI_ATTN_TRACE
+__device__ int g_ap_dbg;
 __device__ long long g_ap_trace[64 * 16];
 #define AP_TRACE(g, slot) do { if (blockIdx.x == 0 && (g) < 64) g_ap_trace[(g) * 16 + (slot)] = clock64(); } while (0)
 #else
@@ -60,6 +61,7 @@ struct AttnPipeParams {
     int nbuf, s_stride, n_obuf, o_col;         // score buffer b at column b*s_stride; O buffer ob at o_col + 64*ob
     int split;                                  // key columns [0, split) -> exp warps 0-3, [split, Np_pad) -> warps 4-7
     int plane_bytes, stages, reverse;
+    int dbg;                                    // experiments (tools/probes, RAJNI_ATTN_TRACE builds only): skip parts of the work
     float scale_log2;
 };
 
@@ -162,6 +164,9 @@ __device__ __forceinline__ float ap_exp_half(uint32_t (&s)[112], bool& have_a, u
     ap_bar_sync(bar_id, 64);                                                  // the two warps that share these 32 rows
     const float mb = fmaxf(mx, *pm_other) * sl2;
     if (trace_lane) AP_TRACE(g, 5);
+#ifdef RAJNI_ATTN_TRACE
+    if (g_ap_dbg & 2) return mb;
+#endif
     float sum0 = 0.f, sum1 = 0.f;
     // p = exp2(s * scale * log2e - max) for R0..R0+16*NCH -> bf16 pairs at W0..
     auto exp_run = [&](auto r0_c, auto w0_c, auto n_c) {
@@ -394,7 +399,11 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
             mbar_wait(&o_full[ob], ob ? o_ph1 : o_ph0);
             tc_fence_after();
             if (hq == 0 && lane == 0) AP_TRACE(e.g, 6);
+#ifdef RAJNI_ATTN_TRACE
+            const bool live = e.j * 128 + hq * 32 < Np && !(p.dbg & 4);
+#else
             const bool live = e.j * 128 + hq * 32 < Np;
+#endif
             uint32_t o0[32], o1[32];
             if (live) {
                 const uint32_t ocol = lane_base + p.o_col + ob * 64;
@@ -452,6 +461,9 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
         for (; c.g < G; c.advance(p)) {
             if (!have_a) mbar_wait(&s_full[c.buf], c.buf_ph);                 // (a prefetched group A has seen this phase complete)
             if (warp == 0 && lane == 0) AP_TRACE(c.g, 8);
+#ifdef RAJNI_ATTN_TRACE
+            if (p.dbg & 1) { __syncwarp(); if (lane == 0) mbar_arrive(&p_full[c.buf]); if (++slot == kApSumSlots) slot = 0; continue; }
+#endif
             if (c.j * 128 + q * 32 < Np) {
                 tc_fence_after();
                 const uint32_t sb = lane_base + c.buf * p.s_stride;
@@ -518,6 +530,10 @@ int launch_attention_pipe(const void* qkv, const int32_t* row_map, void* out, in
     p.row_map = row_map;
     p.N_src = N_src; p.Np = Np; p.Np_pad = Np_pad; p.C = C; p.H = H;
     p.reverse = reverse;
+#ifdef RAJNI_ATTN_TRACE
+    p.dbg = getenv("AP_DEBUG") ? atoi(getenv("AP_DEBUG")) : 0;
+    cudaMemcpyToSymbol(g_ap_dbg, &p.dbg, sizeof(int));
+#endif
     p.BH = B * H;
     p.tpi = Np > 128 ? 2 : 1;
     p.scale_log2 = scale * 1.4426950408889634f;
