@@ -1,9 +1,10 @@
 // a4: C-ABI entry of the attention over kept tokens (attention.py:42-54) and its dispatch to the three tcgen05 kernels.
 //
-//   dense, 128 < Np, Np_pad <= 224 : attention_pipe.cu  (role-pipelined: exp / epilogue / MMA / load warps, S multi-buffered in
-//                                    TMEM, half rows of S held in registers; per-image zero-filled TMA loads)
-//   other Np <= 256                : attention_tc.cu    (two score tiles of 256 columns; gathered calls and Np <= 128, where
-//                                    it is still the faster of the two: profiles/r2_attention_pipe.txt)
+//   128 < Np, Np_pad <= 224, >= 6 (image, head) items per SM : attention_pipe.cu  (role-pipelined: exp / epilogue / MMA / load
+//                                    warps, S multi-buffered in TMEM, half rows of S held in registers): 1.2-1.26x the kernel below
+//                                    at 152..197 tokens and batch 256 (profiles/r2_attention_pipe.md)
+//   other Np <= 256                : attention_tc.cu    (two score tiles of 256 columns; still the faster one for Np <= 128 and for
+//                                    launches of a few items per SM).  The two agree bit for bit.
 //   else                           : attention_long.cu  (key blocks of 224, two passes; the 577-token configuration)
 //
 // RAJNI_ATTN_TC=1 sends every Np <= 256 call to attention_tc.cu, RAJNI_ATTN_PIPE=1 every Np_pad <= 224 call to
@@ -33,7 +34,9 @@ static int attention_dispatch(const void* qkv, const int32_t* row_map, void* out
     if (impl == RAJNI_ATTN_AUTO) {
         static const bool force_tc = getenv("RAJNI_ATTN_TC") != nullptr, force_pipe = getenv("RAJNI_ATTN_PIPE") != nullptr;
         const int np_pad = (Np + 15) & ~15;
-        if (np_pad <= 224 && (force_pipe || (!force_tc && row_map == nullptr && Np > 128))) impl = RAJNI_ATTN_PIPE;
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, current_device());
+        if (np_pad <= 224 && (force_pipe || (!force_tc && Np > 128 && (long long)B * H >= 6LL * sms))) impl = RAJNI_ATTN_PIPE;
         else impl = Np <= 256 ? RAJNI_ATTN_TC : RAJNI_ATTN_LONG;
     }
     int rc = 0;

@@ -29,8 +29,15 @@
 namespace rajni {
 
 constexpr int kApHelpWarp0 = 8;
-constexpr int kApMmaWarp = 12;
-constexpr int kApLoaderWarp0 = 13;
+#ifndef AP_MMA_WARP
+#define AP_MMA_WARP 15
+#endif
+// The MMA issuer sits on scheduler 3 (warp id % 4): its neighbours there are the exp warps of TMEM lanes 96..127, which have
+// no rows at all in the second tile of a 129..224-token item - an issuer next to busy exp warps gets so few issue slots that
+// queueing one P V takes 2200 cycles instead of 1300 (profiles/r2_attention_pipe.md).
+constexpr int kApMmaWarp = AP_MMA_WARP;
+constexpr int kApLoaderWarp0 = 12;                                             // three loader warps: 12..14 (or 13..15)
+constexpr int kApWg3Warp0 = 12;
 constexpr int kApLoaderThreads = 96;
 constexpr int kApLoaderGroups = kApLoaderThreads / 8;                          // 8 lanes move one token's 128-byte head slice
 constexpr int kApSweeps = (224 + kApLoaderGroups - 1) / kApLoaderGroups;       // sweeps of the groups over <= 224 token rows
@@ -38,9 +45,10 @@ constexpr int kApThreads = 512;
 constexpr int kApMaxStages = 4;
 constexpr int kApMaxBufs = 4;
 constexpr int kApSumSlots = 8;
-// Fetch the next tile's first 64 columns under the current tile's last exponentials.  Measured slower on B200 (the tensor pipe
-// spends ~130 cycles per P V k-step, so S(g+1) is rarely complete at the prefetch point and the probe only costs): off.
-constexpr bool kApPrefetch = false;
+#ifndef AP_POLY_EVERY
+#define AP_POLY_EVERY 0
+#endif
+constexpr int kApPolyEvery = AP_POLY_EVERY;               // one exponential in this many is a polynomial on the FMA pipe (0: all on MUFU)
 constexpr int kApOutStage = 4 * 4096;                                          // 32 rows x 128 B per helper warp
 constexpr int kApAuxBytes = 2 * 2 * 128 * 4 + kApSumSlots * 2 * 128 * 4;       // half-row maxima (2 parities), partial row sums
 constexpr int kApBarBytes = 256;
@@ -118,38 +126,47 @@ struct ApCursor {
     }
 };
 
-// One exp-warp thread's share of a tile: the half row [cb, cb + 32*N32 + 16*HAS16) of S (TMEM row `sb`) -> P in place.
+// 2^x on the FMA/ALU pipes (x >= -125 after the clamp): round x to the nearest integer with the 1.5*2^23 trick, a cubic
+// for 2^f on f in [-0.5, 0.5] (relative error 2.2e-4, a twentieth of a bf16 ulp), the integer added into the exponent field.
+// One exponential in kApPolyEvery goes this way: MUFU.EX2 (16 results/clk/SM) is what bounds the exp warps, the FMA pipe idles.
+__device__ __forceinline__ float ap_ex2_poly(float x) {
+    x = fmaxf(x, -125.f);
+    const float t = x + 12582912.f;
+    const float f = x - (t - 12582912.f);
+    float q = fmaf(0.05286743f, f, 0.24215189f);
+    q = fmaf(q, f, 0.69358677f);
+    q = fmaf(q, f, 0.99996275f);
+    return __uint_as_float(__float_as_uint(q) + (__float_as_uint(t) << 23));
+}
+
+// One exp-warp thread's share of a tile: the half row [cb, cb + 32*N32 + 16*HAS16) of S (TMEM row `sb`) -> P at `pcol`.
 // Straight-line for a given (N32, HAS16): no branch between the 16-column groups, so MUFU.EX2 never drains.
-//   Registers: group A = the first two 32-column pieces (s[0..63]), group B = the third piece (s[64..95]) and the
-//   16-column piece (s[96..111]).  The thread holds its WHOLE half row before the row maximum is taken (one wait for all
-//   loads: a tcgen05.ld costs 150-450 cycles whatever its size).  Columns >= Np (at most one partial group) are set to -inf
-//   up front, so neither the maximum nor exp2 needs a mask: exp2(-inf) = 0.
-//   Software pipeline across tiles: once group A's exponentials are packed and stored, group A of the NEXT tile (whose S
-//   the tensor pipe finished long ago, `next_bar`) is fetched into the freed registers under group B's exponentials
-//   (`have_a` tells the next call).  P pair k of a group overwrites the group's register k, consumed by then.
+//   s[0..95] = the 32-column pieces, s[96..111] = the 16-column piece.  The thread holds its WHOLE half row before the row
+//   maximum is taken: one wait for all loads (a tcgen05.ld costs ~150 cycles alone whatever its size), `taken_bar` tells
+//   the MMA issuer that S has left TMEM.  Columns >= Np (fewer than 16, all in the half's last 16 columns) are set to -inf
+//   up front, so neither the maximum nor exp2 needs a mask: exp2(-inf) = 0.  P pair k overwrites register k, consumed by
+//   then; P goes back with at most three stores (a tcgen05.st holds the warp ~100 cycles whatever its size).
+//   drop16: the half's first 16 columns are also the other half's last (both halves run the same width, see the kernel);
+//   they are written (identical values) but not summed.
 // Returns the half row's sum of p.
 template <int N32, int HAS16>
-__device__ __forceinline__ float ap_exp_half(uint32_t (&s)[112], bool& have_a, uint32_t sb, uint32_t sb_next, uint64_t* next_bar,
-                                             uint32_t next_ph, int cb, int Np, float sl2, float* pm_mine, const float* pm_other,
-                                             int bar_id, bool trace_lane, int g) {
-    constexpr int NA = N32 < 2 ? N32 : 2;                                     // 32-column pieces of group A
-    constexpr int NB32 = N32 - NA;                                            // 0 or 1
-    constexpr int WB16 = NB32 ? 80 : 64;                                      // where the 16-column piece's P pairs go
-    if (!have_a) {
+__device__ __forceinline__ float ap_exp_half(uint32_t sb, int cb, uint32_t pcol, int Np, float sl2, float* pm_mine, const float* pm_other,
+                                             int bar_id, int bar_n, uint64_t* taken_bar, bool drop16, int lane, bool trace_lane, int g) {
+    constexpr int NCOL = 32 * N32 + 16 * HAS16;
+    constexpr int LAST = HAS16 ? 96 : 32 * N32 - 16;                          // registers of the half's last 16 columns
+    constexpr int W16 = 16 * N32;                                             // P pairs of the 16-column piece go to s[W16..]
+    uint32_t s[112];
 #pragma unroll
-        for (int i = 0; i < NA; ++i) tmem_ld32(sb + cb + 32 * i, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * i]));
-    }
-    if (NB32) tmem_ld32(sb + cb + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+    for (int i = 0; i < N32; ++i) tmem_ld32(sb + cb + 32 * i, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * i]));
     if (HAS16) tmem_ld16(sb + cb + 32 * N32, *reinterpret_cast<uint32_t(*)[16]>(&s[96]));
     tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(taken_bar);
     if (trace_lane) AP_TRACE(g, 4);
-    if (cb + 32 * N32 + 16 * HAS16 > Np) {                                    // this half holds the padding columns (rare path)
+    if (cb + NCOL > Np) {
 #pragma unroll
-        for (int i = 0; i < 32 * N32; ++i) if (cb + i >= Np) s[i] = 0xff800000u;               // -inf
-        if (HAS16) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) if (cb + 32 * N32 + i >= Np) s[96 + i] = 0xff800000u;
-        }
+        for (int i = 0; i < 16; ++i) if (cb + NCOL - 16 + i >= Np) s[LAST + i] = 0xff800000u;      // -inf
     }
     // ---- row maximum of this half (four independent chains), then of the row (the other half's through shared memory)
     float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -161,54 +178,42 @@ __device__ __forceinline__ float ap_exp_half(uint32_t (&s)[112], bool& have_a, u
     }
     const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
     *pm_mine = mx;
-    ap_bar_sync(bar_id, 64);                                                  // the two warps that share these 32 rows
+    ap_bar_sync(bar_id, bar_n);                                               // the two warps that share these 32 rows
     const float mb = fmaxf(mx, *pm_other) * sl2;
     if (trace_lane) AP_TRACE(g, 5);
 #ifdef RAJNI_ATTN_TRACE
     if (g_ap_dbg & 2) return mb;
 #endif
     float sum0 = 0.f, sum1 = 0.f;
-    // p = exp2(s * scale * log2e - max) for R0..R0+16*NCH -> bf16 pairs at W0..
+    // p = exp2(s * scale * log2e - max) for registers R0..R0+N -> bf16 pairs at W0..; column c of the row takes the
+    // polynomial when c % kApPolyEvery == kApPolyEvery - 1 (cb and R0 are multiples of 16, so the register index decides)
     auto exp_run = [&](auto r0_c, auto w0_c, auto n_c) {
         constexpr int R0 = decltype(r0_c)::value, W0 = decltype(w0_c)::value, N = decltype(n_c)::value;
 #pragma unroll
         for (int j = 0; j < N; j += 2) {
-            const float e0 = ap_ex2(fmaf(__uint_as_float(s[R0 + j]), sl2, -mb));
-            const float e1 = ap_ex2(fmaf(__uint_as_float(s[R0 + j + 1]), sl2, -mb));
+            const float x0 = fmaf(__uint_as_float(s[R0 + j]), sl2, -mb), x1 = fmaf(__uint_as_float(s[R0 + j + 1]), sl2, -mb);
+            const float e0 = ap_ex2(x0);
+            const float e1 = (kApPolyEvery > 0 && (j + 1) % (kApPolyEvery > 0 ? kApPolyEvery : 1) == kApPolyEvery - 1) ? ap_ex2_poly(x1) : ap_ex2(x1);
             sum0 += e0;
             sum1 += e1;
             s[W0 + (j >> 1)] = float2_to_bf16x2(e0, e1);
         }
     };
     using std::integral_constant;
-    // ---- group A
-    exp_run(integral_constant<int, 0>{}, integral_constant<int, 0>{}, integral_constant<int, 32 * NA>{});
-    if (NA == 2) tmem_st32(sb + cb, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-    else if (NA == 1) tmem_st16(sb + cb, *reinterpret_cast<uint32_t(*)[16]>(&s[0]));
-    have_a = false;
-    if (NB32 + HAS16 > 0) {
-        // ---- group B, first 16 columns; then group A of the next tile into the freed registers; then the rest of B
-        constexpr int RB = NB32 ? 64 : 96;
-        exp_run(integral_constant<int, RB>{}, integral_constant<int, 64>{}, integral_constant<int, 16>{});
-        if (kApPrefetch && NA > 0 && next_bar != nullptr && ap_test_uniform(next_bar, next_ph)) {
-            tmem_st_wait();                                                   // P of group A has left its registers
-            tc_fence_after();
-#pragma unroll
-            for (int i = 0; i < NA; ++i) tmem_ld32(sb_next + cb + 32 * i, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * i]));
-            have_a = true;
-        }
-        if (NB32) {
-            exp_run(integral_constant<int, 80>{}, integral_constant<int, 72>{}, integral_constant<int, 16>{});
-            tmem_st16(sb + cb + 32, *reinterpret_cast<uint32_t(*)[16]>(&s[64]));
-            if (HAS16) {
-                exp_run(integral_constant<int, 96>{}, integral_constant<int, WB16>{}, integral_constant<int, 16>{});
-                tmem_st8(sb + cb + 48, *reinterpret_cast<uint32_t(*)[8]>(&s[WB16]));
-            }
-        } else {
-            tmem_st8(sb + cb + 16 * N32, *reinterpret_cast<uint32_t(*)[8]>(&s[64]));
-        }
+    if (N32 > 0) {
+        exp_run(integral_constant<int, 0>{}, integral_constant<int, 0>{}, integral_constant<int, 16>{});
+        if (drop16) { sum0 = 0.f; sum1 = 0.f; }
+        exp_run(integral_constant<int, 16>{}, integral_constant<int, 8>{}, integral_constant<int, 32 * N32 - 16>{});
+    }
+    if (HAS16) {
+        exp_run(integral_constant<int, 96>{}, integral_constant<int, W16>{}, integral_constant<int, 16>{});
+        if (N32 == 0 && drop16) { sum0 = 0.f; sum1 = 0.f; }
     }
     if (trace_lane) AP_TRACE(g, 10);
+    // P pairs are contiguous in s[0 .. NCOL/2): 32 + 16 + 8 columns at most
+    if (NCOL >= 64) tmem_st32(pcol, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+    if ((NCOL / 2) & 16) tmem_st16(pcol + ((NCOL / 2) & 32), *reinterpret_cast<uint32_t(*)[16]>(&s[(NCOL / 2) & 32]));
+    if ((NCOL / 2) & 8) tmem_st8(pcol + ((NCOL / 2) & 48), *reinterpret_cast<uint32_t(*)[8]>(&s[(NCOL / 2) & 48]));
     return sum0 + sum1;
 }
 
@@ -228,6 +233,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
     uint64_t* v_full = bars + 4;                     // [4] loader -> MMA
     uint64_t* stage_empty = bars + 8;                // [4] MMA -> loader (tcgen05.commit after the item's last P V)
     uint64_t* s_full = bars + 12;                    // [4 bufs] MMA -> exp warps (S ready)
+    uint64_t* s_taken = bars + 16;                   // [4 bufs] exp warps -> MMA (S is in registers: the tensor pipe may start P V)
     uint64_t* p_full = bars + 20;                    // [4 bufs] exp warps -> MMA (P in TMEM)
     uint64_t* o_full = bars + 24;                    // [2] MMA -> helpers
     uint64_t* o_empty = bars + 26;                   // [2] helpers -> MMA (O read out)
@@ -247,6 +253,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
             for (int i = 0; i < kApMaxBufs; ++i) {
                 mbar_init(&s_full[i], 1);
                 mbar_init(&p_full[i], 8);            // one arrival per exp warp
+                mbar_init(&s_taken[i], 8);
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&o_full[i], 1);
@@ -265,12 +272,13 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
     const int G = n_mine * p.tpi;                                                          // tiles of this CTA
     const int Np = p.Np, Np_pad = p.Np_pad;
 
-    if (warp >= kApMmaWarp) {
+    if (warp >= kApWg3Warp0) {
       // warpgroup 3 (MMA issuer + loaders) hands registers back: ONE setmaxnreg site for its four warps
       ap_reg_dec<80>();
-      if (warp >= kApLoaderWarp0 && p.row_map == nullptr) {
+      const int lw = warp - kApWg3Warp0 - (warp > kApMmaWarp ? 1 : 0);          // loader warp index 0..2 (the MMA warp aside)
+      if (warp != kApMmaWarp && p.row_map == nullptr) {
         // ================= dense loader: one TMA box per plane; rows past the image's N_src are zero-filled =================
-        if (tid == kApLoaderWarp0 * 32) {
+        if (lw == 0 && lane == 0) {
             tma_prefetch_desc(&tmap_qkv);
             const uint32_t plane_tx = (uint32_t)Np_pad * 128u;
             int stage = 0;
@@ -288,9 +296,9 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
-      } else if (warp >= kApLoaderWarp0) {
+      } else if (warp != kApMmaWarp) {
         // ================= gather loaders: 8 lanes move one token's 128-byte head slice per plane (cp.async) =================
-        const int lt = tid - kApLoaderWarp0 * 32;
+        const int lt = lw * 32 + lane;
         const int grp = lt >> 3, chunk = lt & 7;
         const long long C3 = 3LL * p.C;
         int stage = 0;
@@ -338,6 +346,9 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
             const uint32_t idesc_s = umma_idesc_bf16(128, Np_pad, 0, 0);
             const uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);          // B = V is MN-major
             const int nk = Np_pad / 16, nk0 = p.split / 16;
+            // P of key columns [0, split) sits at the buffer's start; the second half's P (keys Np_pad - split ...) starts at
+            // column `split`, so P of key `split` is (2 split - Np_pad) / 2 columns further in
+            const uint32_t p2 = (uint32_t)(p.split + ((2 * p.split - Np_pad) >> 1));
             const uint64_t qd0 = umma_desc_sw128(smem_base, 16, 1024);
             const uint64_t kd0 = umma_desc_sw128(smem_base + p.plane_bytes, 16, 1024);
             const uint64_t vd0 = umma_desc_sw128(smem_base + 2 * p.plane_bytes, 16, 1024);
@@ -364,6 +375,15 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
             for (int i = 0; i < p.nbuf && s.g < G; ++i) issue_s();
             for (; v.g < G; v.advance(p)) {
                 mbar_wait(&p_full[v.buf], v.buf_ph);
+                // The exp warps read S(v+1) right after P(v); a tcgen05.ld next to the P V products (A operand from TMEM)
+                // takes ~1000 cycles instead of ~300, and slows the products too (profiles/r2_attention_pipe.md), so the
+                // products wait the few hundred cycles until S(v+1) is in registers and then run under the exponentials.
+                if (v.g + 1 < G) {
+                    int nb = v.buf + 1;
+                    uint32_t nph = v.buf_ph;
+                    if (nb == p.nbuf) { nb = 0; nph ^= 1; }
+                    mbar_wait(&s_taken[nb], nph);
+                }
                 mbar_wait(&v_full[v.stage], v.stage_ph);
                 mbar_wait(&o_empty[ob], ob ? o_ph1 : o_ph0);
                 tc_fence_after();
@@ -371,10 +391,9 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
                 const uint64_t vd = vd0 + (uint64_t)((v.stage * stage_bytes) >> 4);
                 const uint32_t pb = tmem_base + v.buf * p.s_stride;
                 const uint32_t d = tmem_base + p.o_col + ob * 64;
-                // P of key columns [0, split) sits at the buffer's start, P of [split, Np_pad) at column `split`
                 uint64_t vdk = vd;
                 for (int k = 0; k < nk0; ++k, vdk += (2048 >> 4)) umma_bf16_ts(d, pb + k * 8, vdk, idesc_o, k != 0);
-                for (int k = 0; k < nk - nk0; ++k, vdk += (2048 >> 4)) umma_bf16_ts(d, pb + p.split + k * 8, vdk, idesc_o, 1);
+                for (int k = 0; k < nk - nk0; ++k, vdk += (2048 >> 4)) umma_bf16_ts(d, pb + p2 + k * 8, vdk, idesc_o, 1);
                 AP_TRACE(v.g, 12);
                 umma_commit(&o_full[ob]);
                 if (v.j == p.tpi - 1) umma_commit(&stage_empty[v.stage]);     // the item's last product: the stage may be refilled
@@ -449,35 +468,34 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
         ap_reg_inc<160>();
         const int q = warp & 3, half = warp >> 2;
         const int row = q * 32 + lane;
-        const int cb = half ? p.split : 0;
-        const int ncol = (half ? Np_pad : p.split) - cb;                      // multiple of 16, <= 112
-        const int nch = ncol >> 4;                                            // 16-column groups of this half (0..7)
+        // Both halves run the SAME width (one code path resident in the instruction cache): `split` columns, the second half
+        // starting at Np_pad - split; where the two overlap (16 columns) the second half does not count them in its sum.
+        // Its P goes to column `split` on, clear of the columns the first half still reads.
+        const int cb = half ? Np_pad - p.split : 0;
+        const int nch = p.split >> 4;                                         // 16-column groups of a half (1..7)
+        const bool drop16 = half && 2 * p.split > Np_pad;
+        const bool has_cols = !half || p.split < Np_pad;                      // (a 16-column row has no second half)
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         const float sl2 = p.scale_log2;
         ApCursor c;
         int slot = 0;
-        uint32_t s[112];                                                      // the half row of S; group A may hold the NEXT tile's
-        bool have_a = false;
         for (; c.g < G; c.advance(p)) {
-            if (!have_a) mbar_wait(&s_full[c.buf], c.buf_ph);                 // (a prefetched group A has seen this phase complete)
+            mbar_wait(&s_full[c.buf], c.buf_ph);
             if (warp == 0 && lane == 0) AP_TRACE(c.g, 8);
 #ifdef RAJNI_ATTN_TRACE
-            if (p.dbg & 1) { __syncwarp(); if (lane == 0) mbar_arrive(&p_full[c.buf]); if (++slot == kApSumSlots) slot = 0; continue; }
+            if (p.dbg & 1) { __syncwarp(); if (lane == 0) { mbar_arrive(&s_taken[c.buf]); mbar_arrive(&p_full[c.buf]); } if (++slot == kApSumSlots) slot = 0; continue; }
 #endif
-            if (c.j * 128 + q * 32 < Np) {
+            if (c.j * 128 + q * 32 < Np && has_cols) {
                 tc_fence_after();
                 const uint32_t sb = lane_base + c.buf * p.s_stride;
-                ApCursor nx = c;
-                nx.advance(p);
-                const bool next_live = nx.g < G && nx.j * 128 + q * 32 < Np;
-                uint64_t* next_bar = next_live ? &s_full[nx.buf] : nullptr;
-                const uint32_t sb_next = lane_base + nx.buf * p.s_stride;
                 float* pm = pmax + (c.g & 1) * 256;
                 float* pm_mine = pm + half * 128 + row;
-                const float* pm_other = pm + (half ^ 1) * 128 + row;
+                const float* pm_other = p.split < Np_pad ? pm + (half ^ 1) * 128 + row : pm_mine;
+                const int bar_n = p.split < Np_pad ? 64 : 32;
                 const bool tl = warp == 0 && lane == 0;
                 float sum;
-#define AP_HALF(N32_, H16_) ap_exp_half<N32_, H16_>(s, have_a, sb, sb_next, next_bar, nx.buf_ph, cb, Np, sl2, pm_mine, pm_other, 1 + q, tl, c.g)
+#define AP_HALF(N32_, H16_) ap_exp_half<N32_, H16_>(sb, cb, sb + (half ? p.split : 0), Np, sl2, pm_mine, pm_other, 1 + q + (bar_n == 32 ? 4 * half : 0), \
+                                                    bar_n, &s_taken[c.buf], drop16, lane, tl, c.g)
                 switch (nch) {                                                // warp-uniform: one straight-line body per width
                     case 7: sum = AP_HALF(3, 1); break;
                     case 6: sum = AP_HALF(3, 0); break;
@@ -485,13 +503,16 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
                     case 4: sum = AP_HALF(2, 0); break;
                     case 3: sum = AP_HALF(1, 1); break;
                     case 2: sum = AP_HALF(1, 0); break;
-                    case 1: sum = AP_HALF(0, 1); break;
-                    default: sum = AP_HALF(0, 0); break;
+                    default: sum = AP_HALF(0, 1); break;
                 }
 #undef AP_HALF
                 sums[(slot * 2 + half) * 128 + row] = sum;
                 tmem_st_wait();
                 tc_fence_before();
+            } else {
+                if (c.j * 128 + q * 32 < Np) sums[(slot * 2 + half) * 128 + row] = 0.f;       // live rows, a half without columns
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_taken[c.buf]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[c.buf]);
