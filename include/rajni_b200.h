@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RAJNI_ABI_VERSION 7
+#define RAJNI_ABI_VERSION 8
 
 enum {
     RAJNI_OK = 0,
@@ -158,6 +158,19 @@ int rajni_patch_im2col(const void* images, int image_dtype, int B, int S, int pa
                        void* cols, const void* cls_pos0, void* x, int C,
                        float* row_stats, long long row_stats_ld, int stats_slots,
                        float cls_sum, float cls_sumsq, const float* norm, void* stream);
+
+/* ---- f3: the loader's Resize(size, bicubic) + CenterCrop(224) on decoded uint8 RGB frames (run.py:62-66), bit-identical
+ * to torchvision on PIL images (Pillow's antialiased two-pass resampler; oracle/resize_oracle.py restates it).
+ * frames: device buffer, the B decoded frames (HWC, uint8) back to back; meta: DEVICE int64 [B][3] = (byte offset of the
+ * frame in `frames`, height, width); max_h >= every height.  out: uint8 [B,3,224,224] planar - what PILToTensor gives after
+ * the two transforms; feed it to rajni_patch_im2col (RAJNI_IMG_U8) for ToTensor + Normalize.
+ * workspace: rajni_resize_workspace_bytes(B, max_h) bytes.  A frame that cannot be handled (shorter edge would end up
+ * below the crop, height above max_h, downscale beyond ~23x) is skipped and reported by rajni_resize_status (which
+ * synchronises the stream): 0 = all frames done, else 1 + index of a rejected frame. */
+size_t rajni_resize_workspace_bytes(int B, int max_h);
+int rajni_resize_center_crop_u8(const void* frames, const long long* meta, int B, int max_h, int size, int crop,
+                                void* out, void* workspace, size_t workspace_bytes, void* stream);
+int rajni_resize_status(const void* workspace, int B, int max_h, void* stream);
 
 #ifdef __cplusplus
 }

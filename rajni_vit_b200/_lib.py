@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "librajni_b200.so")
 RAJNI_OK, RAJNI_EINVAL, RAJNI_ECUDA, RAJNI_EARCH, RAJNI_ERANGE = 0, -1, -2, -3, -4
 ATTN_AUTO, ATTN_PIPE, ATTN_TC, ATTN_LONG = 0, 1, 2, 3
 EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32, EPI_LN_FOLD, EPI_ROW_STATS, HINT_REVERSE_M = 1, 2, 4, 8, 16, 32, 64
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class GemmArgs(Structure):
@@ -51,6 +51,9 @@ SIGNATURES = {
     "rajni_gemm_row_stats_slots": (c_int, [c_int]),
     "rajni_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "rajni_attention_fwd_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
+    "rajni_resize_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "rajni_resize_center_crop_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "rajni_resize_status": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "rajni_patch_im2col": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                    c_void_p, c_longlong, c_int, c_float, c_float, c_void_p, c_void_p]),
 }

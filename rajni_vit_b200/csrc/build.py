@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "librajni_b200.so")
-SOURCES = ["capi.cu", "score_select.cu", "rowops.cu", "gemm_tcgen05.cu", "attention.cu", "attention_pipe.cu", "attention_tc.cu", "attention_long.cu"]
+SOURCES = ["capi.cu", "score_select.cu", "rowops.cu", "resize.cu", "gemm_tcgen05.cu", "attention.cu", "attention_pipe.cu", "attention_tc.cu", "attention_long.cu"]
 HEADERS = ["common.cuh", os.path.join(ROOT, "include", "rajni_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -253,3 +253,34 @@ def patch_im2col(images: torch.Tensor, patch: int, cols: torch.Tensor, cls_pos0:
           _lib.load().rajni_patch_im2col, images.data_ptr(), _IMG_DTYPES[images.dtype], B, S, patch,
           cols.data_ptr(), cls_pos0.data_ptr(), x.data_ptr(), C, _ptr(row_stats),
           0 if row_stats is None else row_stats.shape[1], stats_slots, cls_sum, cls_sumsq, norm_arr, _stream(images))
+
+
+def resize_center_crop(frames: torch.Tensor, meta: torch.Tensor, max_h: int, size: int = 256, crop: int = 224,
+                       out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
+                       check: bool = True) -> torch.Tensor:
+    """Resize(size, bicubic) + CenterCrop(crop) of B decoded uint8 RGB frames (run.py:62-66), bit-identical to torchvision
+    on PIL images.  ``frames``: 1-D uint8 CUDA tensor holding the frames (HWC) back to back; ``meta``: int64 CUDA tensor
+    [B,3] = (byte offset, height, width).  -> uint8 [B,3,crop,crop] (planar, what PILToTensor yields).
+    ``check``: read the status word back (synchronises) and raise for frames the kernel had to skip."""
+    if frames.dtype != torch.uint8 or frames.dim() != 1 or not frames.is_contiguous():
+        raise ValueError("frames must be a contiguous 1-D uint8 tensor")
+    if meta.dtype != torch.int64 or meta.dim() != 2 or meta.shape[1] != 3 or not meta.is_contiguous() or meta.device != frames.device:
+        raise ValueError("meta must be a contiguous int64 [B,3] tensor on the frames' device")
+    B = meta.shape[0]
+    lib = _lib.load()
+    nbytes = int(lib.rajni_resize_workspace_bytes(B, max_h))
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
+    out = torch.empty((B, 3, crop, crop), device=frames.device, dtype=torch.uint8) if out is None else out
+    stream = _stream(frames)
+    src_bytes = frames.numel()
+    _call("resize_center_crop", src_bytes + out.numel(), lib.rajni_resize_center_crop_u8, frames.data_ptr(), meta.data_ptr(),
+          B, max_h, size, crop, out.data_ptr(), workspace.data_ptr(), workspace.numel(), stream)
+    if check:
+        bad = int(lib.rajni_resize_status(workspace.data_ptr(), B, max_h, stream))
+        if bad < 0:
+            _lib.check(bad)
+        if bad:
+            raise ValueError(f"frame {bad - 1} cannot be resized on the GPU (too small for the crop, taller than max_h={max_h}, "
+                             "or a downscale beyond 23x)")
+    return out

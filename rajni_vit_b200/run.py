@@ -12,6 +12,8 @@ Differences from the reference CLI, all deliberate:
   * ``--synthetic N`` replaces the ImageFolder pipeline by N seeded random batches (no dataset, no labels that mean
     anything: accuracy is only a consistency check then);
   * ``--uint8_input`` ships uint8 crops and normalises inside the patch kernel (extension; same logits, 4x fewer H2D bytes);
+  * ``--gpu_preprocess`` leaves only the JPEG decode to the CPU workers: Resize(256, bicubic) + CenterCrop(224) run in
+    ``csrc/resize.cu`` (bit-identical to torchvision on PIL images), ToTensor + Normalize in the patch kernel;
   * ``--ckpt file`` loads timm-named weights from a .safetensors / .pt file (no hub access needed);
   * under torchrun every rank decodes only its shard of each batch (``data.sharded_loader``);
   * without ``timm`` (not installable here) the stand-in ViT with random weights is used and the fact is printed.
@@ -43,9 +45,14 @@ def get_args(argv=None):
     ap.add_argument("--compare_base", action="store_true", help="also evaluate the un-pruned model")
     ap.add_argument("--ckpt", type=str, default=None,
                     help="timm-named ViT weights (.safetensors / .pt) to load instead of timm's hub (rajni_vit_b200.load_checkpoint)")
+    ap.add_argument("--gpu_preprocess", action="store_true",
+                    help="workers only decode; Resize(256, bicubic) + CenterCrop(224) + ToTensor + Normalize run on the GPU "
+                         "(bit-identical to the torchvision pipeline; implies --uint8_input)")
     ap.add_argument("--uint8_input", action="store_true",
                     help="ship uint8 crops to the GPU and normalise inside the patch kernel (4x fewer H2D bytes; same logits)")
     args = ap.parse_args(argv)
+    if args.gpu_preprocess:
+        args.uint8_input = True
     if not args.data_path and args.synthetic <= 0:
         ap.error("give --data_path or --synthetic N")
     return args
@@ -76,6 +83,15 @@ def build_loader(args, image_size: int, rank: int = 0, world: int = 1):
                  torch.randint(0, 1000, (args.batch_size,), generator=g)) for _ in range(args.synthetic)]
     import torchvision.datasets as datasets
     import torchvision.transforms as T
+    if args.gpu_preprocess:
+        if image_size != 224:
+            raise ValueError("--gpu_preprocess: the GPU resize kernel crops to 224 x 224")
+        from .data import GpuPreprocessLoader, collate_frames, decode_only, sharded_loader
+        ds = datasets.ImageFolder(args.data_path, decode_only)
+        kw = dict(num_workers=args.num_workers, pin_memory=False, collate_fn=collate_frames)
+        inner = (sharded_loader(ds, args.batch_size, rank, world, **kw) if world > 1 else
+                 torch.utils.data.DataLoader(ds, batch_size=args.batch_size, shuffle=False, drop_last=False, **kw))
+        return GpuPreprocessLoader(inner, torch.device(args.device if world == 1 else f"cuda:{torch.cuda.current_device()}"))
     tail = [T.PILToTensor()] if args.uint8_input else [T.ToTensor(), T.Normalize(mean=IMAGENET_MEAN, std=IMAGENET_STD)]
     tf = T.Compose([T.Resize(int(image_size * 256 / 224), interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(image_size), *tail])
     ds = datasets.ImageFolder(args.data_path, tf)

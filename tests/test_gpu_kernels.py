@@ -441,3 +441,58 @@ def test_score_select_split_path_is_bit_identical(ops, B, N, H, ratio):
     s0, i0, n0, r0 = ops.score_select(qkv, H, keep, want_scores=True, split=False)
     s1, i1, n1, r1 = ops.score_select(qkv, H, keep, want_scores=True, split=True)
     assert torch.equal(s0, s1) and torch.equal(i0, i1) and torch.equal(n0, n1) and torch.equal(r0, r1)
+
+
+# ------------------------------------------------------------------ f3: Resize(256, bicubic) + CenterCrop(224) on the GPU
+def test_gpu_resize_center_crop_matches_torchvision(ops):
+    """csrc/resize.cu against torchvision on PIL images (run.py:62-66) and against the oracle: bit-exact uint8 crops for a
+    batch of frames of different sizes, portrait and landscape, up- and down-scaled."""
+    np = pytest.importorskip("numpy")
+    Image = pytest.importorskip("PIL.Image")
+    T = pytest.importorskip("torchvision.transforms")
+    from oracle.resize_oracle import resize_center_crop as oracle_resize
+    from rajni_vit_b200.data import gpu_resize_center_crop, pack_frames
+    sizes = [(375, 500), (500, 375), (256, 256), (224, 224), (300, 257), (257, 256), (333, 999), (480, 640), (227, 1500), (1200, 1600), (2048, 1365)]
+    rng = np.random.default_rng(5)
+    frames = []
+    for i, (h, w) in enumerate(sizes):
+        a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if i % 2:
+            a = (np.cumsum(a.astype(np.int32), axis=1) // 5 % 256).astype(np.uint8)
+        frames.append(torch.from_numpy(a))
+    got = gpu_resize_center_crop(frames, "cuda").cpu()
+    tf = T.Compose([T.Resize(256, interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(224), T.PILToTensor()])
+    for i, f in enumerate(frames):
+        ref = tf(Image.fromarray(f.numpy()))
+        assert torch.equal(got[i], ref), f"frame {i} {tuple(f.shape)}: {(got[i].int() - ref.int()).abs().max().item()} off"
+        if i < 4:
+            assert np.array_equal(oracle_resize(f.numpy()), ref.numpy())
+    # frames the kernel cannot take are reported, not silently mangled
+    buf, meta, max_h = pack_frames([frames[0]])
+    with pytest.raises(ValueError, match="cannot be resized"):
+        ops.resize_center_crop(buf.cuda(), meta.cuda(), max_h - 1)
+
+
+def test_gpu_preprocess_loader_feeds_the_wrapper():
+    """GpuPreprocessLoader + set_input_normalization reproduce the reference loader's tensors: logits from raw frames equal
+    the logits from torchvision-preprocessed float images."""
+    np = pytest.importorskip("numpy")
+    Image = pytest.importorskip("PIL.Image")
+    T = pytest.importorskip("torchvision.transforms")
+    import rajni_vit_b200 as pkg
+    from rajni_vit_b200 import run
+    from rajni_vit_b200.data import GpuPreprocessLoader
+    from rajni_vit_b200.vit import create_model
+    rng = np.random.default_rng(9)
+    frames = [torch.from_numpy(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)) for h, w in ((300, 400), (375, 500), (640, 480), (256, 300))]
+    labels = torch.arange(4)
+    loader = GpuPreprocessLoader([(frames, labels)], "cuda")
+    tf = T.Compose([T.Resize(256, interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(224), T.ToTensor(),
+                    T.Normalize(mean=run.IMAGENET_MEAN, std=run.IMAGENET_STD)])
+    ref_images = torch.stack([tf(Image.fromarray(f.numpy())) for f in frames])
+    model = pkg.RAJNIViTWrapper(create_model("vit_tiny_patch16_224", seed=0), {3: {"keep_ratio": 0.8}}).cuda().eval()
+    ref_logits = model(ref_images.cuda())
+    model.set_input_normalization(run.IMAGENET_MEAN, run.IMAGENET_STD)
+    (crops, lab), = list(loader)
+    assert crops.dtype == torch.uint8 and crops.shape == (4, 3, 224, 224) and torch.equal(lab, labels)
+    assert torch.equal(model(crops), ref_logits)

@@ -117,3 +117,24 @@ def test_live_reference_blockwise():
         ref_logits = ref(images)
     assert stats == ref.get_last_stats()
     np.testing.assert_allclose(logits.numpy(), ref_logits.numpy(), atol=2e-5, rtol=1e-4)
+
+
+# ------------------------------------------------------------------ loader: Resize(256, bicubic) + CenterCrop(224)  (run.py:62-66)
+@pytest.mark.parametrize("h,w", [(375, 500), (500, 375), (256, 256), (224, 224), (300, 257), (257, 256), (333, 999), (480, 640), (227, 1500), (768, 1024)])
+def test_resize_oracle_matches_torchvision(h, w):
+    """oracle/resize_oracle.py restates Pillow's antialiased bicubic resampler and torchvision's size / crop rules; it must
+    reproduce torchvision on PIL images bit for bit (this pins the oracle the CUDA kernel is checked against)."""
+    np = pytest.importorskip("numpy")
+    Image = pytest.importorskip("PIL.Image")
+    T = pytest.importorskip("torchvision.transforms")
+    from oracle.resize_oracle import crop_origin, resize_center_crop, resized_size
+    rng = np.random.default_rng(h * 1000 + w)
+    noise = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    smooth = (np.cumsum(noise.astype(np.int32), axis=1) // 7 % 256).astype(np.uint8)
+    tf = T.Compose([T.Resize(256, interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(224), T.PILToTensor()])
+    for img in (noise, smooth):
+        ref = tf(Image.fromarray(img)).numpy()
+        assert np.array_equal(resize_center_crop(img), ref)
+    nh, nw = resized_size(h, w)
+    assert (nw, nh) == T.Resize(256)(Image.fromarray(noise)).size
+    assert min(crop_origin(nh, nw)) >= 0
