@@ -11,6 +11,8 @@
 // centred norm is computed exactly like the reference without a second HBM pass),
 // and the selection state (radix-select histogram, flags, prefix sums).
 // bf16 tiles in, fp32 arithmetic throughout.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace rajni {
@@ -26,11 +28,37 @@ struct ScoreSelectParams {
     int32_t* keep_idx;          // [B,keep+1] or null (score-only)
     float* next_scores;         // [B,keep+1]
     int32_t* row_map;           // [B*(keep+1)] or null
-    const float* pre_logit;     // [B][H*N] CLS logits already computed by score_stream_kernel, or null
-    const float* pre_vm;        // [B][N*64] head-averaged value rows already computed, or null
     int N, C, H, keep;
     float eps;
 };
+
+// shared memory of one image's tail (statistics + selection)
+struct SelSmem {
+    float* score;        // [N]
+    float* scratch;      // [512] reduction scratch
+    uint32_t* hist;      // [256]
+    int* misc;           // [4]
+    int* warp_off;       // [32]
+    float* mu;           // [64]
+    float* hstat;        // [64] per-head softmax sums
+    float* r;            // [N]
+    float* logit;        // [H][N]
+    float* tail;         // whatever follows (the fused kernel keeps the value rows here)
+};
+__device__ __forceinline__ SelSmem carve_sel_smem(float* smem, int N, int H) {
+    SelSmem s;
+    s.score = smem;
+    s.scratch = s.score + N;
+    s.hist = reinterpret_cast<uint32_t*>(s.scratch + 512);
+    s.misc = reinterpret_cast<int*>(s.hist + 256);
+    s.warp_off = s.misc + 4;
+    s.mu = reinterpret_cast<float*>(s.warp_off + 32);
+    s.hstat = s.mu + 64;
+    s.r = s.hstat + 64;
+    s.logit = s.r + N;
+    s.tail = s.logit + (size_t)H * N;
+    return s;
+}
 
 __device__ __forceinline__ float block_sum(float v, float* scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -166,9 +194,11 @@ __device__ void select_and_emit(const float* score, uint32_t* s_hist, int* s_mis
 // One token row: CLS logits of every head (q pre-scaled) and the head-averaged value row.  Shared by the fused kernel
 // (destinations in shared memory) and the streaming kernel of the split path (destinations in global scratch), so both
 // paths produce bit-identical numbers.
-template <int CPL>
-__device__ __forceinline__ void score_row(const __nv_bfloat16* row, const float (&q)[CPL][8], int lane, int chunks, int C, int H,
-                                          int N, int n, float* logit_dst, float* vm_dst, float inv_h) {
+// The CLS query sits in registers (q) or, where the registers are wanted for a second row in flight, in shared memory
+// (qs: floats 0-3 of chunk j at qs[4*j], floats 4-7 at qs[C/2 + 4*j]; conflict-free 16-byte reads).  Same values, same order.
+template <int CPL, bool kQShared>
+__device__ __forceinline__ void score_row(const __nv_bfloat16* row, const float (&q)[CPL][8], const float* qs, int lane, int chunks,
+                                          int C, int H, int N, int n, float* logit_dst, float* vm_dst, float inv_h) {
     uint4 kk[CPL], vv[CPL];
 #pragma unroll
     for (int i = 0; i < CPL; ++i) {
@@ -182,10 +212,19 @@ __device__ __forceinline__ void score_row(const __nv_bfloat16* row, const float 
     for (int i = 0; i < CPL; ++i) {
         float2 k0 = bf16x2_to_float2(kk[i].x), k1 = bf16x2_to_float2(kk[i].y);
         float2 k2 = bf16x2_to_float2(kk[i].z), k3 = bf16x2_to_float2(kk[i].w);
-        float dot = q[i][0] * k0.x;
-        dot = fmaf(q[i][1], k0.y, dot); dot = fmaf(q[i][2], k1.x, dot); dot = fmaf(q[i][3], k1.y, dot);
-        dot = fmaf(q[i][4], k2.x, dot); dot = fmaf(q[i][5], k2.y, dot); dot = fmaf(q[i][6], k3.x, dot);
-        dot = fmaf(q[i][7], k3.y, dot);
+        float4 qa, qb;
+        if (kQShared) {
+            const int j = min(lane + 32 * i, chunks - 1);
+            qa = *reinterpret_cast<const float4*>(qs + 4 * j);
+            qb = *reinterpret_cast<const float4*>(qs + (C >> 1) + 4 * j);
+        } else {
+            qa = make_float4(q[i][0], q[i][1], q[i][2], q[i][3]);
+            qb = make_float4(q[i][4], q[i][5], q[i][6], q[i][7]);
+        }
+        float dot = qa.x * k0.x;
+        dot = fmaf(qa.y, k0.y, dot); dot = fmaf(qa.z, k1.x, dot); dot = fmaf(qa.w, k1.y, dot);
+        dot = fmaf(qb.x, k2.x, dot); dot = fmaf(qb.y, k2.y, dot); dot = fmaf(qb.z, k3.x, dot);
+        dot = fmaf(qb.w, k3.y, dot);
         // 8 lanes share a head (64 dims = 8 chunks)
         dot += __shfl_xor_sync(0xffffffffu, dot, 1);
         dot += __shfl_xor_sync(0xffffffffu, dot, 2);
@@ -223,31 +262,82 @@ __device__ __forceinline__ void load_cls_query(const __nv_bfloat16* img, int lan
     }
 }
 
-// Split path, kernel 1: when a batch has far fewer images than the GPU has SMs (vit_large at 32 images per GPU), one CTA
-// per image leaves most SMs idle and each CTA latency-bound.  This kernel spreads the K/V pass over (image, 16-row block)
-// CTAs and leaves the per-token results in global scratch; score_select_kernel then starts from them (pre_logit / pre_vm).
-constexpr int kStreamThreads = 256;
-constexpr int kStreamRows = 16;
-template <int CPL>
-__global__ void __launch_bounds__(kStreamThreads) score_stream_kernel(const __nv_bfloat16* qkv, float* logit_g, float* vm_g,
-                                                                      int N, int C, int H) {
-    griddep_launch();
-    griddep_wait();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.y, chunks = C >> 3;
-    const __nv_bfloat16* img = qkv + (size_t)b * N * 3 * C;
-    float q[CPL][8];
-    load_cls_query<CPL>(img, lane, chunks, q);
+// The per-image tail: statistics of the value rows and the CLS logits, scores, selection.  Every thread of a 512-thread CTA
+// calls it after a __syncthreads() that made sm.logit (shared) and vm (shared in the fused kernel, global scratch written by
+// other CTAs of the same launch in the overlapped one: read past L1) complete.  Same instruction order for both, so the two
+// kernels agree bit for bit.
+template <bool kVmGlobal>
+__device__ __forceinline__ float vm_ld(const float* p) { return kVmGlobal ? __ldcg(p) : *p; }
+
+template <bool kVmGlobal>
+__device__ void score_tail(const SelSmem& sm, const float* vm, const ScoreSelectParams& p, int b) {
+    const int N = p.N, H = p.H;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float inv_h = 1.0f / (float)H;
-    float* logit_dst = logit_g + (size_t)b * ((H * N + 3) & ~3);     // per-image stride padded to 16 bytes
-    float* vm_dst = vm_g + (size_t)b * N * kHeadDim;
-    for (int n = blockIdx.x * kStreamRows + warp; n < min(N, (int)(blockIdx.x + 1) * kStreamRows); n += kStreamThreads / 32)
-        score_row<CPL>(img + (size_t)n * 3 * C, q, lane, chunks, C, H, N, n, logit_dst, vm_dst, inv_h);
+    // ---- mean over tokens of the head-averaged value (importance.py:25)
+    {
+        int d = tid & 63, g = tid >> 6;        // 8 groups of 64 threads
+        float acc = 0.f;
+        for (int n = g; n < N; n += kSelThreads / 64) acc += vm_ld<kVmGlobal>(vm + (size_t)n * kHeadDim + d);
+        sm.scratch[g * 64 + d] = acc;
+        __syncthreads();
+        if (tid < 64) {
+            float t = 0.f;
+#pragma unroll
+            for (int gg = 0; gg < kSelThreads / 64; ++gg) t += sm.scratch[gg * 64 + tid];
+            sm.mu[tid] = t / (float)N;
+        }
+        __syncthreads();
+    }
+    // ---- r[n] = || vm[n] - mu ||  (importance.py:27)
+    for (int n = warp; n < N; n += kSelWarps) {
+        float a = vm_ld<kVmGlobal>(vm + (size_t)n * kHeadDim + lane) - sm.mu[lane];
+        float c = vm_ld<kVmGlobal>(vm + (size_t)n * kHeadDim + lane + 32) - sm.mu[lane + 32];
+        float ss = warp_sum(a * a + c * c);
+        if (lane == 0) sm.r[n] = sqrtf(ss);
+    }
+    // ---- per-head softmax statistics over all N tokens (importance.py:20)
+    for (int h = warp; h < H; h += kSelWarps) {
+        float* l = sm.logit + (size_t)h * N;
+        float m = -INFINITY;
+        for (int n = lane; n < N; n += 32) m = fmaxf(m, l[n]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int n = lane; n < N; n += 32) {
+            float e = expf(l[n] - m);
+            l[n] = e;
+            s += e;
+        }
+        s = warp_sum(s);
+        if (lane == 0) sm.hstat[h] = s;
+    }
+    __syncthreads();
+    // ---- z-score of r with the unbiased std (importance.py:28-32)
+    float part = 0.f;
+    for (int n = tid; n < N; n += kSelThreads) part += sm.r[n];
+    const float mu = block_sum(part, sm.scratch) / (float)N;
+    part = 0.f;
+    for (int n = tid; n < N; n += kSelThreads) { float d = sm.r[n] - mu; part += d * d; }
+    const float var = block_sum(part, sm.scratch) / (float)(N - 1);
+    const float sd = sqrtf(var) + p.eps;
+    for (int n = tid; n < N; n += kSelThreads) {
+        float a = 0.f;
+        for (int h = 0; h < H; ++h) a += sm.logit[(size_t)h * N + n] / sm.hstat[h];
+        a *= inv_h;                                                    // importance.py:21
+        float z = (sm.r[n] - mu) / sd;
+        float sc = a * (1.0f / (1.0f + expf(-z)));                     // importance.py:32-34
+        sm.score[n] = sc;
+        if (p.scores_out) p.scores_out[(size_t)b * N + n] = sc;
+    }
+    __syncthreads();
+    if (p.keep_idx != nullptr) select_and_emit(sm.score, sm.hist, sm.misc, sm.warp_off, p, b);
 }
 
 // CPL = 16-byte chunks per lane per plane = ceil(C / 256).
-// 64 registers per thread so that two CTAs (two images) share an SM: with one CTA per SM the 256 images of a batch
-// ran as two latency-bound waves on 148 SMs (57 us at N=197); resident together they take 45 us.
+// One CTA per image, everything in shared memory, no scratch: the stand-alone entry points (rajni_importance, rajni_select,
+// rajni_score_select).  64 registers per thread so that two CTAs (two images) share an SM.  All images of a batch are
+// resident at once and march in lock-step - pass, then tail - so the tail (~25 % of the time) is never hidden; the model path
+// uses score_overlap_kernel below.
 template <int CPL>
 __global__ void __launch_bounds__(kSelThreads, 2) score_select_kernel(const ScoreSelectParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -257,117 +347,101 @@ __global__ void __launch_bounds__(kSelThreads, 2) score_select_kernel(const Scor
 
     griddep_launch();
     griddep_wait();
-    float* s_score = smem;                         // [N]
-    float* s_scratch = s_score + N;                // [64 * 8] reduction scratch (also 16-warp scratch)
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_scratch + 512);   // [256]
-    int* s_misc = reinterpret_cast<int*>(s_hist + 256);                // [4]
-    int* s_warp_off = s_misc + 4;                                      // [32]
-    float* s_mu = reinterpret_cast<float*>(s_warp_off + 32);           // [64]
-    float* s_hstat = s_mu + 64;                                        // [2*H] max, sum per head
-    float* s_r = s_hstat + 64;                                         // [N]
-    float* s_logit = s_r + N;                                          // [H][N]
-    float* s_vm = s_logit + (size_t)H * N;                             // [N][64]
-    // (s_vm start is 16-byte aligned when H*N + 2N is a multiple of 4; we only use scalar access)
-
+    const SelSmem sm = carve_sel_smem(smem, N, H);
     if (p.qkv != nullptr) {
+        float* s_vm = sm.tail;                     // [N][64] (scalar access only)
         const int chunks = C >> 3;                 // 16-byte chunks per plane row
         const __nv_bfloat16* img = p.qkv + (size_t)b * N * 3 * C;
-        const float inv_h = 1.0f / (float)H;
-        if (p.pre_logit != nullptr) {
-            // split path: the K/V pass already ran (score_stream_kernel); fetch its per-token results (L2-resident)
-            const float* gl1 = p.pre_logit + (size_t)b * ((H * N + 3) & ~3);
-            const float4* gl = reinterpret_cast<const float4*>(gl1);
-            const float4* gv = reinterpret_cast<const float4*>(p.pre_vm + (size_t)b * N * kHeadDim);
-            for (int i = tid; i < (H * N) / 4; i += kSelThreads) {
-                const float4 v = __ldg(gl + i);
-                s_logit[4 * i] = v.x; s_logit[4 * i + 1] = v.y; s_logit[4 * i + 2] = v.z; s_logit[4 * i + 3] = v.w;
-            }
-            for (int i = ((H * N) / 4) * 4 + tid; i < H * N; i += kSelThreads) s_logit[i] = __ldg(gl1 + i);
-            for (int i = tid; i < N * kHeadDim / 4; i += kSelThreads) {
-                const float4 v = __ldg(gv + i);
-                s_vm[4 * i] = v.x; s_vm[4 * i + 1] = v.y; s_vm[4 * i + 2] = v.z; s_vm[4 * i + 3] = v.w;
-            }
-        } else {
-            float q[CPL][8];
-            load_cls_query<CPL>(img, lane, chunks, q);
-            // ---- the single HBM pass: one warp per token row, K plane then V plane
+        float q[CPL][8];
+        load_cls_query<CPL>(img, lane, chunks, q);
+        // ---- the single HBM pass: one warp per token row, K plane then V plane
 #pragma unroll 2
-            for (int n = warp; n < N; n += kSelWarps)
-                score_row<CPL>(img + (size_t)n * 3 * C, q, lane, chunks, C, H, N, n, s_logit, s_vm, inv_h);
-        }
+        for (int n = warp; n < N; n += kSelWarps)
+            score_row<CPL, false>(img + (size_t)n * 3 * C, q, nullptr, lane, chunks, C, H, N, n, sm.logit, s_vm, 1.0f / (float)H);
         __syncthreads();
-
-        // ---- mean over tokens of the head-averaged value (importance.py:25)
-        {
-            int d = tid & 63, g = tid >> 6;        // 8 groups of 64 threads
-            float acc = 0.f;
-            for (int n = g; n < N; n += kSelThreads / 64) acc += s_vm[(size_t)n * kHeadDim + d];
-            s_scratch[g * 64 + d] = acc;
-            __syncthreads();
-            if (tid < 64) {
-                float t = 0.f;
-#pragma unroll
-                for (int gg = 0; gg < kSelThreads / 64; ++gg) t += s_scratch[gg * 64 + tid];
-                s_mu[tid] = t / (float)N;
-            }
-            __syncthreads();
-        }
-        // ---- r[n] = || vm[n] - mu ||  (importance.py:27)
-        for (int n = warp; n < N; n += kSelWarps) {
-            float a = s_vm[(size_t)n * kHeadDim + lane] - s_mu[lane];
-            float c = s_vm[(size_t)n * kHeadDim + lane + 32] - s_mu[lane + 32];
-            float ss = warp_sum(a * a + c * c);
-            if (lane == 0) s_r[n] = sqrtf(ss);
-        }
-        // ---- per-head softmax statistics over all N tokens (importance.py:20)
-        for (int h = warp; h < H; h += kSelWarps) {
-            float* l = s_logit + (size_t)h * N;
-            float m = -INFINITY;
-            for (int n = lane; n < N; n += 32) m = fmaxf(m, l[n]);
-            m = warp_max(m);
-            float s = 0.f;
-            for (int n = lane; n < N; n += 32) {
-                float e = expf(l[n] - m);
-                l[n] = e;
-                s += e;
-            }
-            s = warp_sum(s);
-            if (lane == 0) s_hstat[h] = s;
-        }
-        __syncthreads();
-        // ---- z-score of r with the unbiased std (importance.py:28-32)
-        float part = 0.f;
-        for (int n = tid; n < N; n += kSelThreads) part += s_r[n];
-        const float mu = block_sum(part, s_scratch) / (float)N;
-        part = 0.f;
-        for (int n = tid; n < N; n += kSelThreads) { float d = s_r[n] - mu; part += d * d; }
-        const float var = block_sum(part, s_scratch) / (float)(N - 1);
-        const float sd = sqrtf(var) + p.eps;
-        for (int n = tid; n < N; n += kSelThreads) {
-            float a = 0.f;
-            for (int h = 0; h < H; ++h) a += s_logit[(size_t)h * N + n] / s_hstat[h];
-            a *= inv_h;                                                    // importance.py:21
-            float z = (s_r[n] - mu) / sd;
-            float sc = a * (1.0f / (1.0f + expf(-z)));                     // importance.py:32-34
-            s_score[n] = sc;
-            if (p.scores_out) p.scores_out[(size_t)b * N + n] = sc;
-        }
+        score_tail<false>(sm, s_vm, p, b);
     } else {
-        for (int n = tid; n < N; n += kSelThreads) s_score[n] = p.scores_in[(size_t)b * N + n];
+        for (int n = tid; n < N; n += kSelThreads) sm.score[n] = p.scores_in[(size_t)b * N + n];
+        __syncthreads();
+        if (p.keep_idx != nullptr) select_and_emit(sm.score, sm.hist, sm.misc, sm.warp_off, p, b);
     }
-    __syncthreads();
-    if (p.keep_idx != nullptr) select_and_emit(s_score, s_hist, s_misc, s_warp_off, p, b);
 }
 
-static size_t score_smem_bytes(int N, int H, bool with_score) {
+// The model path.  CTA (blk, b) streams rows [blk*rpb, (blk+1)*rpb) of image b - two rows per warp, both in flight - and
+// leaves the per-token results (CLS logits [H][N], head-averaged value rows [N][64], fp32) in scratch, which stays in L2.
+// The CTA that finishes an image's LAST block (a counter per image; it puts the counter back to zero) runs the image's tail
+// from that scratch while the other CTAs on the SM and on the chip keep streaming: pass and tail overlap across images, and
+// the grid is ~7 CTAs per image instead of one, so small batches fill the GPU too.
+struct ScoreScratch {
+    int* count;       // [B] zero before the first launch; every launch leaves it zero
+    float* logit;     // [B][pad4(H*N)]
+    float* vm;        // [B][N*64]
+    int nblk, rpb;    // row blocks per image, rows per block
+};
+
+template <int CPL>
+__global__ void __launch_bounds__(kSelThreads, 2) score_overlap_kernel(const ScoreSelectParams p, const ScoreScratch w) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ int s_last;
+    const int N = p.N, C = p.C, H = p.H;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, blk = blockIdx.x;
+
+    griddep_launch();
+    griddep_wait();
+    const int chunks = C >> 3;
+    const __nv_bfloat16* img = p.qkv + (size_t)b * N * 3 * C;
+    const size_t lstride = ((size_t)H * N + 3) & ~(size_t)3;
+    float* gl = w.logit + (size_t)b * lstride;
+    float* gv = w.vm + (size_t)b * N * kHeadDim;
+    {
+        // CLS query, pre-scaled by 1/8 (exact), into shared memory
+        for (int j = tid; j < chunks; j += kSelThreads) {
+            const uint4 u = ld_stream16(img + j * 8);
+            const float2 a = bf16x2_to_float2(u.x), bb = bf16x2_to_float2(u.y), c = bf16x2_to_float2(u.z), d = bf16x2_to_float2(u.w);
+            *reinterpret_cast<float4*>(smem + 4 * j) = make_float4(a.x * 0.125f, a.y * 0.125f, bb.x * 0.125f, bb.y * 0.125f);
+            *reinterpret_cast<float4*>(smem + (C >> 1) + 4 * j) = make_float4(c.x * 0.125f, c.y * 0.125f, d.x * 0.125f, d.y * 0.125f);
+        }
+        __syncthreads();
+        const float dummy[CPL][8] = {};
+        const int n_end = min(N, (blk + 1) * w.rpb);
+#pragma unroll 2
+        for (int n = blk * w.rpb + warp; n < n_end; n += kSelWarps)
+            score_row<CPL, true>(img + (size_t)n * 3 * C, dummy, smem, lane, chunks, C, H, N, n, gl, gv, 1.0f / (float)H);
+    }
+    __threadfence();                               // this thread's scratch writes are visible device-wide ...
+    __syncthreads();
+    if (tid == 0) {
+        const int old = atomicAdd(&w.count[b], 1); // ... before the arrival is
+        s_last = (old == w.nblk - 1);
+        if (s_last) w.count[b] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const SelSmem sm = carve_sel_smem(smem, N, H);
+    {
+        const float4* g4 = reinterpret_cast<const float4*>(gl);
+        for (int i = tid; i < (H * N) / 4; i += kSelThreads) {
+            const float4 v = __ldcg(g4 + i);
+            sm.logit[4 * i] = v.x; sm.logit[4 * i + 1] = v.y; sm.logit[4 * i + 2] = v.z; sm.logit[4 * i + 3] = v.w;
+        }
+        for (int i = ((H * N) / 4) * 4 + tid; i < H * N; i += kSelThreads) sm.logit[i] = __ldcg(gl + i);
+    }
+    __syncthreads();
+    score_tail<true>(sm, gv, p, b);
+}
+
+static size_t score_smem_bytes(int N, int H, bool with_logit, bool with_vm) {
     size_t floats = (size_t)N + 512 + 256 + 4 + 32 + 64 + 64 + N;
-    if (with_score) floats += (size_t)H * N + (size_t)N * kHeadDim;
+    if (with_logit) floats += (size_t)H * N;
+    if (with_vm) floats += (size_t)N * kHeadDim;
     return floats * sizeof(float);
 }
 
 static int launch_score_select(const ScoreSelectParams& p, int B, cudaStream_t stream) {
     const bool with_score = p.qkv != nullptr;
-    size_t smem = score_smem_bytes(p.N, p.H, with_score);
+    size_t smem = score_smem_bytes(p.N, p.H, with_score, with_score);
     RAJNI_REQUIRE(smem <= 227 * 1024, RAJNI_EINVAL, "score_select: N=%d H=%d needs %zu B of shared memory", p.N, p.H, smem);
     int cpl = with_score ? (p.C + 255) / 256 : 1;
     void (*kern)(const ScoreSelectParams) = nullptr;
@@ -386,27 +460,36 @@ static int launch_score_select(const ScoreSelectParams& p, int B, cudaStream_t s
     return check_launch("score_select");
 }
 
-static size_t split_workspace_floats(int B, int N, int H) {
-    return (size_t)B * (((size_t)H * N + 3) & ~(size_t)3) + (size_t)B * N * kHeadDim;
+constexpr int kOverlapRows = 2 * kSelWarps;        // rows of one CTA: two per warp
+
+static size_t scratch_count_ints(int B) { return ((size_t)B + 3) & ~(size_t)3; }
+static size_t scratch_floats(int B, int N, int H) {
+    return scratch_count_ints(B) + (size_t)B * (((size_t)H * N + 3) & ~(size_t)3) + (size_t)B * N * kHeadDim;
 }
 
-// split path, kernel 1 (see score_stream_kernel)
-static int launch_score_stream(const __nv_bfloat16* qkv, int B, int N, int C, int H, float* ws, cudaStream_t stream) {
-    float* logit_g = ws;
-    float* vm_g = ws + (size_t)B * (((size_t)H * N + 3) & ~(size_t)3);
-    void (*kern)(const __nv_bfloat16*, float*, float*, int, int, int) = nullptr;
-    switch ((C + 255) / 256) {
-        case 1: kern = score_stream_kernel<1>; break;
-        case 2: kern = score_stream_kernel<2>; break;
-        case 3: kern = score_stream_kernel<3>; break;
-        case 4: kern = score_stream_kernel<4>; break;
-        default: RAJNI_REQUIRE(false, RAJNI_EINVAL, "score_select: C=%d > 1024 unsupported", C);
+static int launch_score_overlap(const ScoreSelectParams& p, int B, float* ws, cudaStream_t stream) {
+    ScoreScratch w;
+    w.count = reinterpret_cast<int*>(ws);
+    w.logit = ws + scratch_count_ints(B);
+    w.vm = w.logit + (size_t)B * (((size_t)p.H * p.N + 3) & ~(size_t)3);
+    w.nblk = (p.N + kOverlapRows - 1) / kOverlapRows;
+    w.rpb = (p.N + w.nblk - 1) / w.nblk;
+    size_t smem = std::max(score_smem_bytes(p.N, p.H, true, false), (size_t)p.C * sizeof(float));   // tail state / the CLS query
+    RAJNI_REQUIRE(smem <= 227 * 1024, RAJNI_EINVAL, "score_select: N=%d H=%d needs %zu B of shared memory", p.N, p.H, smem);
+    void (*kern)(const ScoreSelectParams, const ScoreScratch) = nullptr;
+    switch ((p.C + 255) / 256) {
+        case 1: kern = score_overlap_kernel<1>; break;
+        case 2: kern = score_overlap_kernel<2>; break;
+        case 3: kern = score_overlap_kernel<3>; break;
+        case 4: kern = score_overlap_kernel<4>; break;
+        default: RAJNI_REQUIRE(false, RAJNI_EINVAL, "score_select: C=%d > 1024 unsupported", p.C);
     }
-    cudaError_t e = launch_kernel(kern, dim3((N + kStreamRows - 1) / kStreamRows, B), dim3(kStreamThreads), 0, stream, 1,
-                                  qkv, logit_g, vm_g, N, C, H);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "score_select: smem attribute: %s", cudaGetErrorString(e));
+    e = launch_kernel(kern, dim3(w.nblk, B), dim3(kSelThreads), smem, stream, 1, p, w);
     count_launch();
-    RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "score_stream: launch failed: %s", cudaGetErrorString(e));
-    return check_launch("score_stream");
+    RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "score_select: launch failed: %s", cudaGetErrorString(e));
+    return check_launch("score_select");
 }
 
 static int check_score_shape(int B, int N, int C, int H) {
@@ -461,7 +544,7 @@ extern "C" int rajni_score_select(const void* qkv, int B, int N, int C, int H, i
 extern "C" size_t rajni_score_select_workspace_bytes(int B, int N, int C, int H) {
     (void)C;
     if (B <= 0 || N <= 0 || H <= 0) return 0;
-    return split_workspace_floats(B, N, H) * sizeof(float);
+    return scratch_floats(B, N, H) * sizeof(float);
 }
 
 extern "C" int rajni_score_select_split(const void* qkv, int B, int N, int C, int H, int keep, float eps,
@@ -474,15 +557,10 @@ extern "C" int rajni_score_select_split(const void* qkv, int B, int N, int C, in
     RAJNI_REQUIRE(B <= 65535, RAJNI_EINVAL, "rajni_score_select_split: B=%d exceeds the grid limit", B);
     RAJNI_REQUIRE(workspace_bytes >= rajni_score_select_workspace_bytes(B, N, C, H) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
                   RAJNI_EINVAL, "rajni_score_select_split: workspace too small (%zu B) or not 16-byte aligned", workspace_bytes);
-    float* ws = static_cast<float*>(workspace);
-    auto s = static_cast<cudaStream_t>(stream);
-    if (int rc = launch_score_stream(static_cast<const __nv_bfloat16*>(qkv), B, N, C, H, ws, s)) return rc;
     ScoreSelectParams p{};
     p.qkv = static_cast<const __nv_bfloat16*>(qkv);
     p.scores_out = scores;
     p.keep_idx = keep_idx; p.next_scores = next_scores; p.row_map = row_map;
-    p.pre_logit = ws;
-    p.pre_vm = ws + (size_t)B * (((size_t)H * N + 3) & ~(size_t)3);
     p.N = N; p.C = C; p.H = H; p.keep = keep; p.eps = eps;
-    return launch_score_select(p, B, s);
+    return launch_score_overlap(p, B, static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
 }
