@@ -77,14 +77,9 @@ int rajni_score_select(const void* qkv, int B, int N, int C, int H, int keep, fl
                        float* scores, int32_t* keep_idx, float* next_scores,
                        int32_t* row_map, void* stream);
 
-/* Same result, bit for bit, from the overlapped kernel the model path uses: ~N/32 CTAs per image stream the K/V planes into
- * `workspace` (per-token CLS logits and head-averaged value rows, L2-resident); the CTA that finishes an image's last row
- * block runs that image's statistics and selection while the rest of the grid keeps streaming, so the pass and the tail
- * overlap across images and small batches still fill the GPU.  ONE launch.
- * workspace: rajni_score_select_workspace_bytes(B,N,C,H) bytes, 16-byte aligned, caller-owned.  Its first B ints are the
- * per-image arrival counters: they must be ZERO before the first launch (cudaMemset the buffer once) and every launch
- * leaves them zero again, so the buffer is reusable across calls and shapes.  Launches that may run concurrently (different
- * streams) need different workspaces. */
+/* Same result, bit for bit, in two launches for batches with far fewer images than the GPU has SMs (one CTA per image
+ * would leave most SMs idle): the K/V pass is spread over (image, 16-row block) CTAs into `workspace`
+ * (rajni_score_select_workspace_bytes(B,N,C,H) bytes, 16-byte aligned, caller-owned), then the per-image kernel finishes. */
 size_t rajni_score_select_workspace_bytes(int B, int N, int C, int H);
 int rajni_score_select_split(const void* qkv, int B, int N, int C, int H, int keep, float eps,
                              float* scores, int32_t* keep_idx, float* next_scores, int32_t* row_map,

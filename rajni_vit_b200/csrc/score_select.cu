@@ -20,6 +20,18 @@ namespace rajni {
 constexpr int kSelThreads = 512;
 constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kHeadDim = 64;
+constexpr int kVmSmemStride = kHeadDim + 1;     // value rows in shared memory: thread-per-row reads without bank conflicts
+
+// Optional event trace (tools/probes/score_trace.cu builds this file with -DRAJNI_SCORE_TRACE): globaltimer stamps (ns) of
+// one CTA's thread 0.
+#ifdef RAJNI_SCORE_TRACE
+__device__ long long g_sc_trace[64 * 16];
+__device__ int g_sc_trace_cta;
+__device__ __forceinline__ long long sc_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define SC_TRACE(row, slot) do { if (threadIdx.x == 0 && (int)blockIdx.x == g_sc_trace_cta && (row) < 64) g_sc_trace[(row) * 16 + (slot)] = sc_now(); } while (0)
+#else
+#define SC_TRACE(row, slot) do { } while (0)
+#endif
 
 struct ScoreSelectParams {
     const __nv_bfloat16* qkv;   // [B,N,3C] or null (select-only)
@@ -28,6 +40,8 @@ struct ScoreSelectParams {
     int32_t* keep_idx;          // [B,keep+1] or null (score-only)
     float* next_scores;         // [B,keep+1]
     int32_t* row_map;           // [B*(keep+1)] or null
+    const float* pre_logit;     // [B][pad4(H*N)] CLS logits already computed by score_stream_kernel, or null
+    const float* pre_vm;        // [B][N*64] head-averaged value rows already computed, or null
     int N, C, H, keep;
     float eps;
 };
@@ -41,31 +55,44 @@ struct SelSmem {
     int* warp_off;       // [32]
     float* mu;           // [64]
     float* hstat;        // [64] per-head softmax sums
-    float* r;            // [N]
+    float* r;            // [N rounded up to 4] first: 16-byte aligned
     float* logit;        // [H][N]
     float* tail;         // whatever follows (the fused kernel keeps the value rows here)
 };
 __device__ __forceinline__ SelSmem carve_sel_smem(float* smem, int N, int H) {
     SelSmem s;
-    s.score = smem;
+    s.r = smem;                                    // 16-byte aligned, room for N rounded up to 4 (the selection keys)
+    s.score = s.r + ((N + 3) & ~3);
     s.scratch = s.score + N;
     s.hist = reinterpret_cast<uint32_t*>(s.scratch + 512);
     s.misc = reinterpret_cast<int*>(s.hist + 256);
     s.warp_off = s.misc + 4;
     s.mu = reinterpret_cast<float*>(s.warp_off + 32);
     s.hstat = s.mu + 64;
-    s.r = s.hstat + 64;
-    s.logit = s.r + N;
+    s.logit = s.hstat + 64;
     s.tail = s.logit + (size_t)H * N;
     return s;
 }
 
-__device__ __forceinline__ float block_sum(float v, float* scratch) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    v = warp_sum(v);
-    __syncthreads();                       // scratch may still be read from a previous call
-    if (lane == 0) scratch[warp] = v;
-    __syncthreads();
+// The tail's arithmetic is written for 512 "virtual" threads (16 virtual warps) so that a CTA of NT = 512 or 256 real threads
+// produces the same bits: thread t plays virtual threads t, t + NT, ...; a virtual warp is always one real warp.
+// Sum over the virtual threads of f(v): warp tree, then the 16 warp totals through a second warp tree.
+// barrier of the NT threads that run a tail: the whole CTA, or (overlapped kernel) its compute warps on named barrier 1
+template <int NT>
+__device__ __forceinline__ void tail_sync() {
+    if (NT == kSelThreads) __syncthreads();
+    else asm volatile("bar.sync 1, %0;" :: "n"(NT) : "memory");
+}
+
+template <int NT, typename F>
+__device__ __forceinline__ float block_sum(F f, float* scratch) {
+    const int lane = threadIdx.x & 31;
+    tail_sync<NT>();                       // scratch may still be read from a previous call
+    for (int v = threadIdx.x; v < kSelThreads; v += NT) {
+        const float x = warp_sum(f(v));
+        if (lane == 0) scratch[v >> 5] = x;
+    }
+    tail_sync<NT>();
     float t = (lane < kSelWarps) ? scratch[lane] : 0.f;
     return warp_sum(t);                    // every warp reduces the same 16 values
 }
@@ -80,6 +107,7 @@ __device__ __forceinline__ uint32_t float_key(float f) {
 
 // Select the `keep` largest of score[1..N-1] (ties: lower index first), always keep token 0,
 // and emit ascending indices.  All threads of the CTA call this; score[] is in smem.
+template <int NT>
 __device__ void select_and_emit(const float* score, uint32_t* s_hist, int* s_misc, int* s_warp_off,
                                 const ScoreSelectParams& p, int b) {
     const int N = p.N, keep = p.keep, tid = threadIdx.x;
@@ -87,13 +115,13 @@ __device__ void select_and_emit(const float* score, uint32_t* s_hist, int* s_mis
     uint32_t prefix = 0, mask = 0;
     int remaining = keep;
     for (int shift = 24; shift >= 0; shift -= 8) {
-        if (tid < 256) s_hist[tid] = 0;
-        __syncthreads();
-        for (int n = 1 + tid; n < N; n += kSelThreads) {
+        for (int i = tid; i < 256; i += NT) s_hist[i] = 0;
+        tail_sync<NT>();
+        for (int n = 1 + tid; n < N; n += NT) {
             uint32_t k = float_key(score[n]);
             if ((k & mask) == prefix) atomicAdd(&s_hist[(k >> shift) & 0xff], 1u);
         }
-        __syncthreads();
+        tail_sync<NT>();
         if (tid < 32) {
             // warp 0: each lane owns 8 consecutive bins, highest bins in lane 0
             uint32_t c[8];
@@ -119,17 +147,17 @@ __device__ void select_and_emit(const float* score, uint32_t* s_hist, int* s_mis
                 }
             }
         }
-        __syncthreads();
+        tail_sync<NT>();
         prefix |= (uint32_t)s_misc[0] << shift;
         mask |= 0xffu << shift;
         remaining = s_misc[1];
-        __syncthreads();
+        tail_sync<NT>();
     }
     const uint32_t thresh = prefix;        // exact key of the keep-th largest
     // `remaining` of the elements equal to thresh are kept, lowest index first.
 
     // ---- flags + ascending compaction. Thread t owns tokens [t*ipt, (t+1)*ipt).
-    const int ipt = (N + kSelThreads - 1) / kSelThreads;
+    const int ipt = (N + NT - 1) / NT;
     const int n0 = tid * ipt;
     int n_gt = 0, n_eq = 0;
     for (int i = 0; i < ipt; ++i) {
@@ -151,18 +179,18 @@ __device__ void select_and_emit(const float* score, uint32_t* s_hist, int* s_mis
         if (lane >= o) incl += t;
     }
     if (lane == 31) s_warp_off[warp] = incl;
-    __syncthreads();
+    tail_sync<NT>();
     if (warp == 0) {
-        int w = (lane < kSelWarps) ? s_warp_off[lane] : 0;
+        int w = (lane < NT / 32) ? s_warp_off[lane] : 0;
         int wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, wi, o);
             if (lane >= o) wi += t;
         }
-        if (lane < kSelWarps) s_warp_off[lane] = wi - w;   // exclusive warp offsets
+        if (lane < NT / 32) s_warp_off[lane] = wi - w;   // exclusive warp offsets
     }
-    __syncthreads();
+    tail_sync<NT>();
     int excl = incl - packed + s_warp_off[warp];
     int gt_before = excl >> 16, eq_before = excl & 0xffff;
     const int stride = keep + 1;
@@ -191,22 +219,27 @@ __device__ void select_and_emit(const float* score, uint32_t* s_hist, int* s_mis
     }
 }
 
-// One token row: CLS logits of every head (q pre-scaled) and the head-averaged value row.  Shared by the fused kernel
-// (destinations in shared memory) and the streaming kernel of the split path (destinations in global scratch), so both
-// paths produce bit-identical numbers.
-// The CLS query sits in registers (q) or, where the registers are wanted for a second row in flight, in shared memory
-// (qs: floats 0-3 of chunk j at qs[4*j], floats 4-7 at qs[C/2 + 4*j]; conflict-free 16-byte reads).  Same values, same order.
-template <int CPL, bool kQShared>
-__device__ __forceinline__ void score_row(const __nv_bfloat16* row, const float (&q)[CPL][8], const float* qs, int lane, int chunks,
-                                          int C, int H, int N, int n, float* logit_dst, float* vm_dst, float inv_h) {
-    uint4 kk[CPL], vv[CPL];
+// One token row: CLS logits of every head (q pre-scaled) and the head-averaged value row.  Shared by the one-CTA-per-image
+// kernel (destinations in shared memory) and the overlapped kernel (destinations in global scratch), so both produce
+// bit-identical numbers.  Loads and arithmetic are separate so that a warp can have several rows in flight.
+template <int CPL>
+__device__ __forceinline__ void score_row_load(const __nv_bfloat16* row, int lane, int chunks, int C, bool live,
+                                               uint4 (&kk)[CPL], uint4 (&vv)[CPL]) {
 #pragma unroll
     for (int i = 0; i < CPL; ++i) {
         int j = lane + 32 * i;
-        bool ok = j < chunks;
+        bool ok = live && j < chunks;
         kk[i] = ok ? ld_stream16(row + C + j * 8) : make_uint4(0, 0, 0, 0);
         vv[i] = ok ? ld_stream16(row + 2 * C + j * 8) : make_uint4(0, 0, 0, 0);
     }
+}
+
+// The CLS query sits in registers (q, pre-scaled floats) or as the raw bf16 row in shared memory (qs; unpacked and scaled by
+// 1/8 on the fly: the same values).
+template <int CPL, bool kQShared>
+__device__ __forceinline__ void score_row_math(const uint4 (&kk)[CPL], const uint4 (&vv)[CPL], const float (&q)[CPL][8], const uint4* qs,
+                                               int lane, int chunks, int C, int H, int N, int n, float* logit_dst, float* vm_dst,
+                                               int vm_stride, float inv_h) {
     float va[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < CPL; ++i) {
@@ -214,9 +247,10 @@ __device__ __forceinline__ void score_row(const __nv_bfloat16* row, const float 
         float2 k2 = bf16x2_to_float2(kk[i].z), k3 = bf16x2_to_float2(kk[i].w);
         float4 qa, qb;
         if (kQShared) {
-            const int j = min(lane + 32 * i, chunks - 1);
-            qa = *reinterpret_cast<const float4*>(qs + 4 * j);
-            qb = *reinterpret_cast<const float4*>(qs + (C >> 1) + 4 * j);
+            const uint4 u = qs[min(lane + 32 * i, chunks - 1)];
+            const float2 a = bf16x2_to_float2(u.x), bb = bf16x2_to_float2(u.y), c = bf16x2_to_float2(u.z), d = bf16x2_to_float2(u.w);
+            qa = make_float4(a.x * 0.125f, a.y * 0.125f, bb.x * 0.125f, bb.y * 0.125f);
+            qb = make_float4(c.x * 0.125f, c.y * 0.125f, d.x * 0.125f, d.y * 0.125f);
         } else {
             qa = make_float4(q[i][0], q[i][1], q[i][2], q[i][3]);
             qb = make_float4(q[i][4], q[i][5], q[i][6], q[i][7]);
@@ -243,10 +277,18 @@ __device__ __forceinline__ void score_row(const __nv_bfloat16* row, const float 
         va[e] += __shfl_xor_sync(0xffffffffu, va[e], 16);
     }
     if (lane < 8) {
-        float* dst = vm_dst + (size_t)n * kHeadDim + lane * 8;
+        float* dst = vm_dst + (size_t)n * vm_stride + lane * 8;
 #pragma unroll
         for (int e = 0; e < 8; ++e) dst[e] = va[e] * inv_h;       // importance.py:24
     }
+}
+
+template <int CPL>
+__device__ __forceinline__ void score_row(const __nv_bfloat16* row, const float (&q)[CPL][8], int lane, int chunks,
+                                          int C, int H, int N, int n, float* logit_dst, float* vm_dst, int vm_stride, float inv_h) {
+    uint4 kk[CPL], vv[CPL];
+    score_row_load<CPL>(row, lane, chunks, C, true, kk, vv);
+    score_row_math<CPL, false>(kk, vv, q, nullptr, lane, chunks, C, H, N, n, logit_dst, vm_dst, vm_stride, inv_h);
 }
 
 // CLS query of the image, pre-scaled by 1/sqrt(64) (exact: power of two)
@@ -262,42 +304,119 @@ __device__ __forceinline__ void load_cls_query(const __nv_bfloat16* img, int lan
     }
 }
 
-// The per-image tail: statistics of the value rows and the CLS logits, scores, selection.  Every thread of a 512-thread CTA
-// calls it after a __syncthreads() that made sm.logit (shared) and vm (shared in the fused kernel, global scratch written by
-// other CTAs of the same launch in the overlapped one: read past L1) complete.  Same instruction order for both, so the two
-// kernels agree bit for bit.
-template <bool kVmGlobal>
-__device__ __forceinline__ float vm_ld(const float* p) { return kVmGlobal ? __ldcg(p) : *p; }
+// Selection for N <= 256 (every 224-px configuration): rank by counting instead of four radix passes with their twelve
+// block barriers.  Thread n counts the patches with a larger key (keys in shared memory, read four at a time; slot 0 and the
+// padding hold key 0, which no score maps to); equal keys - rare - are found through a counter per rank and ordered by index
+// in a second loop only their threads run.  Positions come from one ballot per warp.  Same output as select_and_emit.
+template <int NT>
+__device__ void select_rank_emit(const float* score, uint32_t* key, uint32_t* s_cnt, int* s_warp_cnt, const ScoreSelectParams& p, int b) {
+    const int N = p.N, keep = p.keep, tid = threadIdx.x, lane = tid & 31;
+    const int N4 = (N + 3) & ~3;
+    for (int n = tid; n < N4; n += NT) key[n] = (n >= 1 && n < N) ? float_key(score[n]) : 0u;
+    for (int i = tid; i < 256; i += NT) s_cnt[i] = 0;
+    tail_sync<NT>();
+    const int n = tid;                                   // N <= 256 <= NT
+    const uint32_t kn = (n >= 1 && n < N) ? key[n] : 0xffffffffu;
+    int gt = 0;
+    {
+        const uint4* k4 = reinterpret_cast<const uint4*>(key);
+#pragma unroll 4
+        for (int m = 0; m < N4 / 4; ++m) {
+            const uint4 k = k4[m];
+            gt += (k.x > kn) + (k.y > kn) + (k.z > kn) + (k.w > kn);
+        }
+    }
+    if (n >= 1 && n < N) atomicAdd(&s_cnt[gt], 1u);      // gt <= N - 2 <= 254
+    tail_sync<NT>();
+    bool take = false;
+    if (n == 0) {
+        take = true;                                     // CLS is always kept
+    } else if (n < N) {
+        int rank = gt;
+        if (s_cnt[gt] > 1u && gt < keep) {               // tied with other patches: lower index first
+            for (int m = 1; m < n; ++m) rank += (key[m] == kn);
+        }
+        take = rank < keep;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, take);
+    if (lane == 0) s_warp_cnt[tid >> 5] = __popc(bal);
+    tail_sync<NT>();
+    if (take) {
+        int pos = __popc(bal & ((1u << lane) - 1u));
+        for (int w = 0; w < (tid >> 5); ++w) pos += s_warp_cnt[w];
+        const size_t o = (size_t)b * (keep + 1) + pos;
+        p.keep_idx[o] = n;
+        p.next_scores[o] = score[n];
+        if (p.row_map) p.row_map[o] = b * N + n;
+    }
+}
 
+template <int NT>
+__device__ __forceinline__ void select_any(const SelSmem& sm, const ScoreSelectParams& p, int b) {
+    // sm.r is dead by now: its N (+3, the scratch after it is free too) words hold the keys
+    if (p.N <= 256) select_rank_emit<NT>(sm.score, reinterpret_cast<uint32_t*>(sm.r), sm.hist, sm.warp_off, p, b);
+    else select_and_emit<NT>(sm.score, sm.hist, sm.misc, sm.warp_off, p, b);
+}
+
+// squared distance of one value row from mu; four interleaved partial sums, the same order whether the row is read from
+// shared memory or (16-byte loads past L1) from the scratch other CTAs of the launch wrote
 template <bool kVmGlobal>
-__device__ void score_tail(const SelSmem& sm, const float* vm, const ScoreSelectParams& p, int b) {
+__device__ __forceinline__ float row_dist2(const float* row, const float* mu) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kHeadDim / 4; ++i) {
+        float4 v;
+        if (kVmGlobal) v = __ldcg(reinterpret_cast<const float4*>(row) + i);
+        else v = make_float4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
+        const float d0 = v.x - mu[4 * i], d1 = v.y - mu[4 * i + 1], d2 = v.z - mu[4 * i + 2], d3 = v.w - mu[4 * i + 3];
+        a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1); a2 = fmaf(d2, d2, a2); a3 = fmaf(d3, d3, a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
+// The per-image tail: statistics of the value rows and the CLS logits, scores, selection.  The NT threads that run it (the
+// CTA's 512, or the 448 of the overlapped kernel's compute warps: same bits, see block_sum) call it after a barrier that made
+// sm.logit (shared) and vm complete:
+// rows of `vs` floats in shared memory, or - long sequences in the overlapped kernel - the global scratch written by other
+// CTAs of the launch (read past L1).  Thread-per-token wherever the reference's reductions allow: ~9 block barriers in all.
+template <int NT, bool kVmGlobal>
+__device__ void score_tail(const SelSmem& sm, const float* vm, const ScoreSelectParams& p, int b, int trace_row = 0) {
     const int N = p.N, H = p.H;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int vs = kVmGlobal ? kHeadDim : kVmSmemStride;
     const float inv_h = 1.0f / (float)H;
-    // ---- mean over tokens of the head-averaged value (importance.py:25)
+    SC_TRACE(32 + trace_row, 4);
+    // ---- mean over tokens of the head-averaged value (importance.py:25): 8 interleaved partial sums per dim, then their sum
     {
-        int d = tid & 63, g = tid >> 6;        // 8 groups of 64 threads
-        float acc = 0.f;
-        for (int n = g; n < N; n += kSelThreads / 64) acc += vm_ld<kVmGlobal>(vm + (size_t)n * kHeadDim + d);
-        sm.scratch[g * 64 + d] = acc;
-        __syncthreads();
+        const int d = tid & 63;
+        for (int g = tid >> 6; g < kSelThreads / 64; g += NT / 64) {
+            float acc = 0.f;
+            int n = g;
+            for (; n + 24 < N; n += 32) {            // four rows in flight (the global reads are L2 round trips)
+                const float x0 = kVmGlobal ? __ldcg(vm + (size_t)n * vs + d) : vm[(size_t)n * vs + d];
+                const float x1 = kVmGlobal ? __ldcg(vm + (size_t)(n + 8) * vs + d) : vm[(size_t)(n + 8) * vs + d];
+                const float x2 = kVmGlobal ? __ldcg(vm + (size_t)(n + 16) * vs + d) : vm[(size_t)(n + 16) * vs + d];
+                const float x3 = kVmGlobal ? __ldcg(vm + (size_t)(n + 24) * vs + d) : vm[(size_t)(n + 24) * vs + d];
+                acc += x0; acc += x1; acc += x2; acc += x3;
+            }
+            for (; n < N; n += 8) acc += kVmGlobal ? __ldcg(vm + (size_t)n * vs + d) : vm[(size_t)n * vs + d];
+            sm.scratch[g * 64 + d] = acc;
+        }
+        tail_sync<NT>();
         if (tid < 64) {
             float t = 0.f;
 #pragma unroll
             for (int gg = 0; gg < kSelThreads / 64; ++gg) t += sm.scratch[gg * 64 + tid];
             sm.mu[tid] = t / (float)N;
         }
-        __syncthreads();
+        tail_sync<NT>();
     }
-    // ---- r[n] = || vm[n] - mu ||  (importance.py:27)
-    for (int n = warp; n < N; n += kSelWarps) {
-        float a = vm_ld<kVmGlobal>(vm + (size_t)n * kHeadDim + lane) - sm.mu[lane];
-        float c = vm_ld<kVmGlobal>(vm + (size_t)n * kHeadDim + lane + 32) - sm.mu[lane + 32];
-        float ss = warp_sum(a * a + c * c);
-        if (lane == 0) sm.r[n] = sqrtf(ss);
-    }
-    // ---- per-head softmax statistics over all N tokens (importance.py:20)
-    for (int h = warp; h < H; h += kSelWarps) {
+    SC_TRACE(32 + trace_row, 5);
+    // ---- r[n] = || vm[n] - mu ||  (importance.py:27): thread per token
+    for (int n = tid; n < N; n += NT) sm.r[n] = sqrtf(row_dist2<kVmGlobal>(vm + (size_t)n * vs, sm.mu));
+    SC_TRACE(32 + trace_row, 6);
+    // ---- per-head softmax statistics over all N tokens (importance.py:20): warp per head
+    for (int h = warp; h < H; h += NT / 32) {
         float* l = sm.logit + (size_t)h * N;
         float m = -INFINITY;
         for (int n = lane; n < N; n += 32) m = fmaxf(m, l[n]);
@@ -311,16 +430,16 @@ __device__ void score_tail(const SelSmem& sm, const float* vm, const ScoreSelect
         s = warp_sum(s);
         if (lane == 0) sm.hstat[h] = s;
     }
-    __syncthreads();
+    SC_TRACE(32 + trace_row, 7);
     // ---- z-score of r with the unbiased std (importance.py:28-32)
-    float part = 0.f;
-    for (int n = tid; n < N; n += kSelThreads) part += sm.r[n];
-    const float mu = block_sum(part, sm.scratch) / (float)N;
-    part = 0.f;
-    for (int n = tid; n < N; n += kSelThreads) { float d = sm.r[n] - mu; part += d * d; }
-    const float var = block_sum(part, sm.scratch) / (float)(N - 1);
+    const float* r = sm.r;
+    const float mu = block_sum<NT>([&](int v) { float t = 0.f; for (int n = v; n < N; n += kSelThreads) t += r[n]; return t; },
+                                   sm.scratch) / (float)N;
+    const float var = block_sum<NT>([&](int v) { float t = 0.f; for (int n = v; n < N; n += kSelThreads) { float d = r[n] - mu; t += d * d; } return t; },
+                                    sm.scratch) / (float)(N - 1);
     const float sd = sqrtf(var) + p.eps;
-    for (int n = tid; n < N; n += kSelThreads) {
+    SC_TRACE(32 + trace_row, 8);
+    for (int n = tid; n < N; n += NT) {
         float a = 0.f;
         for (int h = 0; h < H; ++h) a += sm.logit[(size_t)h * N + n] / sm.hstat[h];
         a *= inv_h;                                                    // importance.py:21
@@ -329,15 +448,18 @@ __device__ void score_tail(const SelSmem& sm, const float* vm, const ScoreSelect
         sm.score[n] = sc;
         if (p.scores_out) p.scores_out[(size_t)b * N + n] = sc;
     }
-    __syncthreads();
-    if (p.keep_idx != nullptr) select_and_emit(sm.score, sm.hist, sm.misc, sm.warp_off, p, b);
+    tail_sync<NT>();
+    SC_TRACE(32 + trace_row, 9);
+    if (p.keep_idx != nullptr) select_any<NT>(sm, p, b);
+    SC_TRACE(32 + trace_row, 10);
 }
 
 // CPL = 16-byte chunks per lane per plane = ceil(C / 256).
 // One CTA per image, everything in shared memory, no scratch: the stand-alone entry points (rajni_importance, rajni_select,
 // rajni_score_select).  64 registers per thread so that two CTAs (two images) share an SM.  All images of a batch are
-// resident at once and march in lock-step - pass, then tail - so the tail (~25 % of the time) is never hidden; the model path
-// uses score_overlap_kernel below.
+// resident at once and march in lock-step - pass, then tail - so the tail (~25 % of the time) is never hidden.  A persistent
+// kernel that overlaps the two across images was built and measured (tools/probes/score_overlap_persistent_experiment.patch,
+// profiles/r2_score_select.md): the tail's ~8 us latency is still exposed after the last image, so it did not win.
 template <int CPL>
 __global__ void __launch_bounds__(kSelThreads, 2) score_select_kernel(const ScoreSelectParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -352,90 +474,66 @@ __global__ void __launch_bounds__(kSelThreads, 2) score_select_kernel(const Scor
         float* s_vm = sm.tail;                     // [N][64] (scalar access only)
         const int chunks = C >> 3;                 // 16-byte chunks per plane row
         const __nv_bfloat16* img = p.qkv + (size_t)b * N * 3 * C;
-        float q[CPL][8];
-        load_cls_query<CPL>(img, lane, chunks, q);
-        // ---- the single HBM pass: one warp per token row, K plane then V plane
+        if (p.pre_logit != nullptr) {
+            // split path: the K/V pass already ran (score_stream_kernel); fetch its per-token results (L2-resident) in one
+            // round trip - every load of the copy is independent
+            const float* gl1 = p.pre_logit + (size_t)b * (((size_t)H * N + 3) & ~(size_t)3);
+            const float4* gl = reinterpret_cast<const float4*>(gl1);
+            const float4* gv = reinterpret_cast<const float4*>(p.pre_vm + (size_t)b * N * kHeadDim);
+            for (int i = tid; i < (H * N) / 4; i += kSelThreads) {
+                const float4 v = __ldg(gl + i);
+                sm.logit[4 * i] = v.x; sm.logit[4 * i + 1] = v.y; sm.logit[4 * i + 2] = v.z; sm.logit[4 * i + 3] = v.w;
+            }
+            for (int i = ((H * N) / 4) * 4 + tid; i < H * N; i += kSelThreads) sm.logit[i] = __ldg(gl1 + i);
+#pragma unroll 8
+            for (int i = tid; i < N * kHeadDim / 4; i += kSelThreads) {
+                const float4 v = __ldg(gv + i);
+                float* dst = s_vm + (i >> 4) * kVmSmemStride + 4 * (i & 15);
+                dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+            }
+        } else {
+            float q[CPL][8];
+            load_cls_query<CPL>(img, lane, chunks, q);
+            // ---- the single HBM pass: one warp per token row, K plane then V plane
 #pragma unroll 2
-        for (int n = warp; n < N; n += kSelWarps)
-            score_row<CPL, false>(img + (size_t)n * 3 * C, q, nullptr, lane, chunks, C, H, N, n, sm.logit, s_vm, 1.0f / (float)H);
+            for (int n = warp; n < N; n += kSelWarps)
+                score_row<CPL>(img + (size_t)n * 3 * C, q, lane, chunks, C, H, N, n, sm.logit, s_vm, kVmSmemStride, 1.0f / (float)H);
+        }
         __syncthreads();
-        score_tail<false>(sm, s_vm, p, b);
+        score_tail<kSelThreads, false>(sm, s_vm, p, b);
     } else {
         for (int n = tid; n < N; n += kSelThreads) sm.score[n] = p.scores_in[(size_t)b * N + n];
         __syncthreads();
-        if (p.keep_idx != nullptr) select_and_emit(sm.score, sm.hist, sm.misc, sm.warp_off, p, b);
+        if (p.keep_idx != nullptr) select_any<kSelThreads>(sm, p, b);
     }
 }
 
-// The model path.  CTA (blk, b) streams rows [blk*rpb, (blk+1)*rpb) of image b - two rows per warp, both in flight - and
-// leaves the per-token results (CLS logits [H][N], head-averaged value rows [N][64], fp32) in scratch, which stays in L2.
-// The CTA that finishes an image's LAST block (a counter per image; it puts the counter back to zero) runs the image's tail
-// from that scratch while the other CTAs on the SM and on the chip keep streaming: pass and tail overlap across images, and
-// the grid is ~7 CTAs per image instead of one, so small batches fill the GPU too.
-struct ScoreScratch {
-    int* count;       // [B] zero before the first launch; every launch leaves it zero
-    float* logit;     // [B][pad4(H*N)]
-    float* vm;        // [B][N*64]
-    int nblk, rpb;    // row blocks per image, rows per block
-};
-
+// Split path, kernel 1: when a batch has far fewer images than the GPU has SMs (vit_large at 32 images per GPU), one CTA
+// per image leaves most SMs idle and each CTA latency-bound.  This kernel spreads the K/V pass over (image, 16-row block)
+// CTAs and leaves the per-token results in global scratch; score_select_kernel then starts from them (pre_logit / pre_vm).
+constexpr int kStreamThreads = 256;
+constexpr int kStreamRows = 16;
 template <int CPL>
-__global__ void __launch_bounds__(kSelThreads, 2) score_overlap_kernel(const ScoreSelectParams p, const ScoreScratch w) {
-    extern __shared__ __align__(16) float smem[];
-    __shared__ int s_last;
-    const int N = p.N, C = p.C, H = p.H;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y, blk = blockIdx.x;
-
+__global__ void __launch_bounds__(kStreamThreads) score_stream_kernel(const __nv_bfloat16* qkv, float* logit_g, float* vm_g,
+                                                                      int N, int C, int H) {
     griddep_launch();
     griddep_wait();
-    const int chunks = C >> 3;
-    const __nv_bfloat16* img = p.qkv + (size_t)b * N * 3 * C;
-    const size_t lstride = ((size_t)H * N + 3) & ~(size_t)3;
-    float* gl = w.logit + (size_t)b * lstride;
-    float* gv = w.vm + (size_t)b * N * kHeadDim;
-    {
-        // CLS query, pre-scaled by 1/8 (exact), into shared memory
-        for (int j = tid; j < chunks; j += kSelThreads) {
-            const uint4 u = ld_stream16(img + j * 8);
-            const float2 a = bf16x2_to_float2(u.x), bb = bf16x2_to_float2(u.y), c = bf16x2_to_float2(u.z), d = bf16x2_to_float2(u.w);
-            *reinterpret_cast<float4*>(smem + 4 * j) = make_float4(a.x * 0.125f, a.y * 0.125f, bb.x * 0.125f, bb.y * 0.125f);
-            *reinterpret_cast<float4*>(smem + (C >> 1) + 4 * j) = make_float4(c.x * 0.125f, c.y * 0.125f, d.x * 0.125f, d.y * 0.125f);
-        }
-        __syncthreads();
-        const float dummy[CPL][8] = {};
-        const int n_end = min(N, (blk + 1) * w.rpb);
-#pragma unroll 2
-        for (int n = blk * w.rpb + warp; n < n_end; n += kSelWarps)
-            score_row<CPL, true>(img + (size_t)n * 3 * C, dummy, smem, lane, chunks, C, H, N, n, gl, gv, 1.0f / (float)H);
-    }
-    __threadfence();                               // this thread's scratch writes are visible device-wide ...
-    __syncthreads();
-    if (tid == 0) {
-        const int old = atomicAdd(&w.count[b], 1); // ... before the arrival is
-        s_last = (old == w.nblk - 1);
-        if (s_last) w.count[b] = 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const SelSmem sm = carve_sel_smem(smem, N, H);
-    {
-        const float4* g4 = reinterpret_cast<const float4*>(gl);
-        for (int i = tid; i < (H * N) / 4; i += kSelThreads) {
-            const float4 v = __ldcg(g4 + i);
-            sm.logit[4 * i] = v.x; sm.logit[4 * i + 1] = v.y; sm.logit[4 * i + 2] = v.z; sm.logit[4 * i + 3] = v.w;
-        }
-        for (int i = ((H * N) / 4) * 4 + tid; i < H * N; i += kSelThreads) sm.logit[i] = __ldcg(gl + i);
-    }
-    __syncthreads();
-    score_tail<true>(sm, gv, p, b);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, chunks = C >> 3;
+    const __nv_bfloat16* img = qkv + (size_t)b * N * 3 * C;
+    float q[CPL][8];
+    load_cls_query<CPL>(img, lane, chunks, q);
+    const float inv_h = 1.0f / (float)H;
+    float* logit_dst = logit_g + (size_t)b * (((size_t)H * N + 3) & ~(size_t)3);     // per-image stride padded to 16 bytes
+    float* vm_dst = vm_g + (size_t)b * N * kHeadDim;
+    for (int n = blockIdx.x * kStreamRows + warp; n < min(N, (int)(blockIdx.x + 1) * kStreamRows); n += kStreamThreads / 32)
+        score_row<CPL>(img + (size_t)n * 3 * C, q, lane, chunks, C, H, N, n, logit_dst, vm_dst, kHeadDim, inv_h);
 }
 
 static size_t score_smem_bytes(int N, int H, bool with_logit, bool with_vm) {
-    size_t floats = (size_t)N + 512 + 256 + 4 + 32 + 64 + 64 + N;
+    size_t floats = (size_t)((N + 3) & ~3) + N + 512 + 256 + 4 + 32 + 64 + 64;
     if (with_logit) floats += (size_t)H * N;
-    if (with_vm) floats += (size_t)N * kHeadDim;
+    if (with_vm) floats += (size_t)N * kVmSmemStride;
     return floats * sizeof(float);
 }
 
@@ -460,36 +558,27 @@ static int launch_score_select(const ScoreSelectParams& p, int B, cudaStream_t s
     return check_launch("score_select");
 }
 
-constexpr int kOverlapRows = 2 * kSelWarps;        // rows of one CTA: two per warp
-
-static size_t scratch_count_ints(int B) { return ((size_t)B + 3) & ~(size_t)3; }
-static size_t scratch_floats(int B, int N, int H) {
-    return scratch_count_ints(B) + (size_t)B * (((size_t)H * N + 3) & ~(size_t)3) + (size_t)B * N * kHeadDim;
+static size_t split_workspace_floats(int B, int N, int H) {
+    return (size_t)B * (((size_t)H * N + 3) & ~(size_t)3) + (size_t)B * N * kHeadDim;
 }
 
-static int launch_score_overlap(const ScoreSelectParams& p, int B, float* ws, cudaStream_t stream) {
-    ScoreScratch w;
-    w.count = reinterpret_cast<int*>(ws);
-    w.logit = ws + scratch_count_ints(B);
-    w.vm = w.logit + (size_t)B * (((size_t)p.H * p.N + 3) & ~(size_t)3);
-    w.nblk = (p.N + kOverlapRows - 1) / kOverlapRows;
-    w.rpb = (p.N + w.nblk - 1) / w.nblk;
-    size_t smem = std::max(score_smem_bytes(p.N, p.H, true, false), (size_t)p.C * sizeof(float));   // tail state / the CLS query
-    RAJNI_REQUIRE(smem <= 227 * 1024, RAJNI_EINVAL, "score_select: N=%d H=%d needs %zu B of shared memory", p.N, p.H, smem);
-    void (*kern)(const ScoreSelectParams, const ScoreScratch) = nullptr;
-    switch ((p.C + 255) / 256) {
-        case 1: kern = score_overlap_kernel<1>; break;
-        case 2: kern = score_overlap_kernel<2>; break;
-        case 3: kern = score_overlap_kernel<3>; break;
-        case 4: kern = score_overlap_kernel<4>; break;
-        default: RAJNI_REQUIRE(false, RAJNI_EINVAL, "score_select: C=%d > 1024 unsupported", p.C);
+// split path, kernel 1 (see score_stream_kernel)
+static int launch_score_stream(const __nv_bfloat16* qkv, int B, int N, int C, int H, float* ws, cudaStream_t stream) {
+    float* logit_g = ws;
+    float* vm_g = ws + (size_t)B * (((size_t)H * N + 3) & ~(size_t)3);
+    void (*kern)(const __nv_bfloat16*, float*, float*, int, int, int) = nullptr;
+    switch ((C + 255) / 256) {
+        case 1: kern = score_stream_kernel<1>; break;
+        case 2: kern = score_stream_kernel<2>; break;
+        case 3: kern = score_stream_kernel<3>; break;
+        case 4: kern = score_stream_kernel<4>; break;
+        default: RAJNI_REQUIRE(false, RAJNI_EINVAL, "score_select: C=%d > 1024 unsupported", C);
     }
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "score_select: smem attribute: %s", cudaGetErrorString(e));
-    e = launch_kernel(kern, dim3(w.nblk, B), dim3(kSelThreads), smem, stream, 1, p, w);
+    cudaError_t e = launch_kernel(kern, dim3((N + kStreamRows - 1) / kStreamRows, B), dim3(kStreamThreads), 0, stream, 1,
+                                  qkv, logit_g, vm_g, N, C, H);
     count_launch();
-    RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "score_select: launch failed: %s", cudaGetErrorString(e));
-    return check_launch("score_select");
+    RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "score_stream: launch failed: %s", cudaGetErrorString(e));
+    return check_launch("score_stream");
 }
 
 static int check_score_shape(int B, int N, int C, int H) {
@@ -544,7 +633,7 @@ extern "C" int rajni_score_select(const void* qkv, int B, int N, int C, int H, i
 extern "C" size_t rajni_score_select_workspace_bytes(int B, int N, int C, int H) {
     (void)C;
     if (B <= 0 || N <= 0 || H <= 0) return 0;
-    return scratch_floats(B, N, H) * sizeof(float);
+    return split_workspace_floats(B, N, H) * sizeof(float);
 }
 
 extern "C" int rajni_score_select_split(const void* qkv, int B, int N, int C, int H, int keep, float eps,
@@ -557,10 +646,15 @@ extern "C" int rajni_score_select_split(const void* qkv, int B, int N, int C, in
     RAJNI_REQUIRE(B <= 65535, RAJNI_EINVAL, "rajni_score_select_split: B=%d exceeds the grid limit", B);
     RAJNI_REQUIRE(workspace_bytes >= rajni_score_select_workspace_bytes(B, N, C, H) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
                   RAJNI_EINVAL, "rajni_score_select_split: workspace too small (%zu B) or not 16-byte aligned", workspace_bytes);
+    float* ws = static_cast<float*>(workspace);
+    auto s = static_cast<cudaStream_t>(stream);
+    if (int rc = launch_score_stream(static_cast<const __nv_bfloat16*>(qkv), B, N, C, H, ws, s)) return rc;
     ScoreSelectParams p{};
     p.qkv = static_cast<const __nv_bfloat16*>(qkv);
     p.scores_out = scores;
     p.keep_idx = keep_idx; p.next_scores = next_scores; p.row_map = row_map;
+    p.pre_logit = ws;
+    p.pre_vm = ws + (size_t)B * (((size_t)H * N + 3) & ~(size_t)3);
     p.N = N; p.C = C; p.H = H; p.keep = keep; p.eps = eps;
-    return launch_score_overlap(p, B, static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
+    return launch_score_select(p, B, s);
 }

@@ -98,18 +98,13 @@ def select(scores: torch.Tensor, keep: int, keep_idx=None, next_scores=None, row
     return keep_idx, next_scores, row_map
 
 
+SPLIT_SCORE_MAX_BATCH = 96      # below this many images per launch the K/V pass is spread over (image, row-block) CTAs
 _score_ws = {}
 
 
 def score_workspace_bytes(B: int, N: int, C: int, num_heads: int) -> int:
-    """Scratch bytes of the overlapped score path (rajni_score_select_workspace_bytes)."""
+    """Scratch bytes the split score path needs (rajni_score_select_workspace_bytes)."""
     return int(_lib.load().rajni_score_select_workspace_bytes(B, N, C, num_heads))
-
-
-def score_workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
-    """A scratch buffer for rajni_score_select_split: ZERO-filled (its head holds the per-image arrival counters, which every
-    launch leaves at zero again)."""
-    return torch.zeros(nbytes, device=dev, dtype=torch.uint8)
 
 
 def _score_workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
@@ -118,7 +113,7 @@ def _score_workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
     buffers stay alive in the list.  RAJNIViTWrapper owns its scratch (``workspace=``) and does not come here."""
     bufs = _score_ws.setdefault(dev, [])
     if not bufs or bufs[-1].numel() < nbytes:
-        bufs.append(score_workspace(dev, nbytes))
+        bufs.append(torch.empty(nbytes, device=dev, dtype=torch.uint8))
     return bufs[-1]
 
 
@@ -127,12 +122,8 @@ def score_select(qkv: torch.Tensor, num_heads: int, keep: int, eps: float = 1e-6
                  workspace: Optional[torch.Tensor] = None):
     """Fused importance + selection on qkv [B,N,3C] bf16.
     Returns (scores or None, keep_idx, next_scores, row_map).
-    ``split`` (default True): the overlapped kernel - ~7 CTAs per image stream the K/V planes into ``workspace``, the last
-    one to finish an image runs its statistics and selection while the others keep streaming.  False: the stand-alone
-    one-CTA-per-image kernel (no scratch).  Bit-identical results.
-    ``workspace``: from ``score_workspace(dev, score_workspace_bytes(B, N, C, H))`` (zero-filled once, reusable); a caller
-    that replays CUDA graphs must pass one it owns, so that the captured address lives as long as the graph.  Two launches
-    that may run CONCURRENTLY (different streams) need different workspaces."""
+    ``workspace``: uint8 scratch of at least ``score_workspace_bytes(B, N, C, H)`` for the split path (small batches); a
+    caller that replays CUDA graphs must pass one it owns, so that the captured address lives as long as the graph."""
     _bf16c(qkv)
     B, N, C3 = qkv.shape
     dev = qkv.device
@@ -144,7 +135,7 @@ def score_select(qkv: torch.Tensor, num_heads: int, keep: int, eps: float = 1e-6
     C = C3 // 3
     lib = _lib.load()
     if split is None:
-        split = True
+        split = B <= SPLIT_SCORE_MAX_BATCH
     # algorithmic bytes: K and V planes + CLS query in, index + carried score out
     work = B * (2 * N * C * 2 + C * 2 + 8 * (keep + 1))
     if split:

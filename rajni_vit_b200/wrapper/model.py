@@ -165,9 +165,9 @@ class RAJNIViTWrapper(nn.Module):
             stat_slots=ops.row_stats_slots(C),
             stats=torch.zeros((ops.row_stats_slots(C), B * N0, 2), device=dev, dtype=torch.float32),
             sel={},
-            # scratch of the score kernel (zero-filled: arrival counters): owned here, so a captured graph's pointer lives
-            # with the graph
-            score_ws=ops.score_workspace(dev, max(ops.score_workspace_bytes(B, N0, C, blk.attn.num_heads) for blk in self.blocks)),
+            # scratch of the split score path (small batches): owned here, so a captured graph's pointer lives with the graph
+            score_ws=(torch.empty(max(ops.score_workspace_bytes(B, N0, C, blk.attn.num_heads) for blk in self.blocks),
+                                  device=dev, dtype=torch.uint8) if B <= ops.SPLIT_SCORE_MAX_BATCH else None),
         )
         self._ws = {key: ws}        # keep one shape resident
         self._graphs = {}           # a captured graph points into the workspace it was captured with

@@ -434,26 +434,14 @@ def test_reverse_traversal_hints_do_not_change_results(ops):
 
 
 @pytest.mark.parametrize("B,N,H,ratio", [(8, 197, 12, 0.88), (3, 577, 12, 0.88), (5, 197, 6, 0.7), (4, 197, 16, 0.9),
-                                         (300, 197, 12, 0.8), (2, 33, 3, 0.5), (7, 32, 2, 0.9), (1, 2, 1, 1.0)])
+                                         (300, 197, 12, 0.8), (2, 33, 3, 0.5), (7, 32, 2, 0.9), (1, 2, 1, 1.0), (2, 257, 3, 0.6)])
 def test_score_select_split_path_is_bit_identical(ops, B, N, H, ratio):
-    """The overlapped kernel of the model path (rajni_score_select_split: row-block CTAs + last-arriver tail over scratch)
-    must reproduce the one-CTA-per-image kernel exactly - and leave its scratch reusable (arrival counters back at zero):
-    the second and third calls run on the same workspace, the third with another shape."""
+    """The two-launch path for small batches (rajni_score_select_split) must reproduce the fused kernel exactly."""
     qkv = dev(make_qkv(B, N, H, 64, 900 + N + H), torch.bfloat16)
     keep = max(1, min(N - 1, orc.keep_count(N, ratio)))
     s0, i0, n0, r0 = ops.score_select(qkv, H, keep, want_scores=True, split=False)
-    ws = ops.score_workspace(qkv.device, ops.score_workspace_bytes(B, N, H * 64, H))
-    for _ in range(2):
-        s1, i1, n1, r1 = ops.score_select(qkv, H, keep, want_scores=True, split=True, workspace=ws)
-        assert torch.equal(s0, s1) and torch.equal(i0, i1) and torch.equal(n0, n1) and torch.equal(r0, r1)
-    if B > 1 and N > 8:
-        Bs, Ns = B - 1, N - 5
-        q2 = qkv[:Bs, :Ns].contiguous()
-        k2 = max(1, keep - 6)
-        a = ops.score_select(q2, H, k2, want_scores=True, split=False)
-        b = ops.score_select(q2, H, k2, want_scores=True, split=True, workspace=ws)
-        assert all(torch.equal(x, y) for x, y in zip(a, b))
-    assert int(ws[: 4 * B].view(torch.int32).abs().sum()) == 0
+    s1, i1, n1, r1 = ops.score_select(qkv, H, keep, want_scores=True, split=True)
+    assert torch.equal(s0, s1) and torch.equal(i0, i1) and torch.equal(n0, n1) and torch.equal(r0, r1)
 
 
 # ------------------------------------------------------------------ f3: Resize(256, bicubic) + CenterCrop(224) on the GPU

@@ -1,6 +1,5 @@
 """score_select at the per-GPU batches of the 8-GPU configs (C3: vit_small bs 64, C4: vit_large bs 32, C5: deit-384 bs 16):
-the overlapped kernel of the model path (row-block CTAs + last-arriver tail, `split=True`) against the one-CTA-per-image kernel.
-Every case rotates over enough distinct qkv buffers to exceed the 126 MB L2, so the K/V pass comes from HBM."""
+split path (K/V pass spread over (image, row-block) CTAs + per-image selection kernel) against the fused one-CTA-per-image kernel."""
 import os
 import sys
 
@@ -33,7 +32,7 @@ def timeit(fn, inner=50, iters=7):
 for name, B, N, H, r in (("C3 vit_small bs64", 64, 197, 6, 0.7), ("C3 late layer", 64, 60, 6, 0.7), ("C4 vit_large bs32", 32, 197, 16, 0.9),
                          ("C4 late layer", 32, 40, 16, 0.9), ("C5 deit384 bs16", 16, 577, 12, 0.88), ("C2 bs256", 256, 197, 12, 0.88)):
     keep = max(1, int(r * (N - 1)))
-    nbuf = max(1, min(4, int(400e6 // (B * N * 3 * H * 64 * 2)) + 1))
+    nbuf = max(1, min(4, int(400e6 // (B * N * 3 * H * 64 * 2)) + 1))     # rotate over > 126 MB of inputs: the pass comes from HBM
     qkvs = [torch.randn(B, N, 3 * H * 64, device="cuda").bfloat16() for _ in range(nbuf)]
     out = {}
     it = [0]
@@ -46,4 +45,4 @@ for name, B, N, H, r in (("C3 vit_small bs64", 64, 197, 6, 0.7), ("C3 late layer
             ops.score_select(qkvs[it[0] % nbuf], H, keep, keep_idx=idx, next_scores=nxt, row_map=rmap, split=split)
         out[split] = timeit(call, inner=48)
     mb = B * (2 * N * H * 64 * 2) / 1e6
-    print(f"{name:20s} B={B:3d} N={N:3d} C={H*64:4d}: overlapped {out[True]:6.1f} us   one CTA per image {out[False]:6.1f} us   ({mb:6.1f} MB of K,V = {mb/6.4e3*1e3:5.1f} us at HBM peak)", flush=True)
+    print(f"{name:20s} B={B:3d} N={N:3d} C={H*64:4d}: split {out[True]:6.1f} us   fused {out[False]:6.1f} us   ({mb:6.1f} MB of K,V = {mb/6.4e3*1e3:5.1f} us at HBM peak)", flush=True)
