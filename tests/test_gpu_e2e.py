@@ -398,3 +398,31 @@ def test_trained_like_checkpoint_end_to_end(pkg, tmp_path, name, sched, batch, s
         ov, worst = near_tie_mismatch(kidx, rec["scores"], kidx.shape[1] - 1, 0.06)
         print(f"  block {rec['block']}: kept-set overlap {ov:.4f}, worst disagreeing token {worst:.2e} from the cut")
         assert worst < 0.06 and ov > 0.98
+
+
+# ------------------------------------------------------------------ f4: schedule sweep / search on the device
+def test_schedule_sweep_and_search(pkg):
+    """rajni_vit_b200.schedule on a small stand-in: the dense model agrees with itself, every candidate reports the
+    token counts its schedule implies, pruning lowers the tensor work, labels switch the accuracy axis to top-1, and the
+    greedy search returns a schedule at or above its floor."""
+    from rajni_vit_b200 import schedule as S
+    from rajni_vit_b200.vit import create_model
+    make = lambda: create_model("vit_micro_patch16_64", seed=0)                    # noqa: E731
+    depth = len(make().blocks)
+    g = torch.Generator().manual_seed(3)
+    batches = [torch.randn(16, 3, 64, 64, generator=g) for _ in range(2)]
+    res = S.sweep(make, batches, candidates=[("dense", {}), ("half", {1: {"keep_ratio": 0.5}}),
+                                              ("carried", {1: {"keep_ratio": 0.7}, 2: {"keep_ratio": 0.7, "update": False}})])
+    assert res[0]["agreement"] == 100.0 and res[0]["top1"] is None and res[0]["accuracy"] == 100.0
+    for r in res:
+        assert r["token_counts"] == S.token_counts(r["schedule"], depth, 17) and r["img_s"] > 0
+        assert 0.0 <= r["agreement"] <= 100.0
+    assert res[1]["gflop_per_image"] < res[0]["gflop_per_image"]
+    assert [r["name"] for r in S.pareto_front(res)][-1] == "dense" or res[0]["img_s"] >= max(r["img_s"] for r in res)
+    # labels: the accuracy axis becomes top-1 against them (here: the dense model's own predictions -> 100 % for dense)
+    labels = [p.cpu() for p in res[0]["predictions"]]
+    lab = S.measure(make, {}, list(zip(batches, labels)))
+    assert lab["top1"] == 100.0 and lab["accuracy"] == 100.0
+    sched, hist = S.search(make, batches, floor=50.0, ratios=(1.0, 0.75, 0.5), timing_steps=3)
+    assert hist[0]["schedule"] == {} and all(h["accuracy"] >= 50.0 for h in hist)
+    assert sched == hist[-1]["schedule"]

@@ -275,3 +275,53 @@ def test_load_checkpoint_rejects_what_the_wrapper_cannot_run(tmp_path):
         pkg.load_checkpoint(clash)
     with pytest.raises(KeyError, match="not a timm-named"):
         pkg.load_checkpoint({"encoder.layer.0.weight": torch.ones(2)})
+
+
+# ------------------------------------------------------------------ f4: schedule search (host logic)
+def test_schedule_token_counts_and_flops_match_the_bench_constants():
+    from rajni_vit_b200 import schedule as S
+    readme = {3: {"keep_ratio": .88}, 4: {"keep_ratio": .88}, 7: {"keep_ratio": .8}, 8: {"keep_ratio": .72}}
+    counts = S.token_counts(readme, 12, 197)
+    assert counts == [197, 197, 197, 197, 173, 152, 152, 152, 121, 87, 87, 87]
+    assert S.token_counts({}, 12, 197) == [197] * 12
+    assert S.token_counts({0: {"keep_ratio": 0.001}}, 2, 50) == [50, 2]          # one patch + CLS survive
+    # 25.332 GFLOP/image: the figure bench.py and DESIGN.md quote for C2 (SURVEY 8d formula)
+    assert abs(S.flops_per_image(counts, 768, 3072, 196) / 1e9 - 25.332) < 5e-3
+    assert S.flops_per_image(counts, 768, 3072, 196) < S.flops_per_image([197] * 12, 768, 3072, 196)
+
+
+def test_pareto_front_and_candidate_grid():
+    from rajni_vit_b200 import schedule as S
+    rs = [dict(name="a", img_s=10, accuracy=80.0), dict(name="b", img_s=20, accuracy=79.0), dict(name="c", img_s=15, accuracy=78.0),
+          dict(name="d", img_s=30, accuracy=60.0), dict(name="e", img_s=30, accuracy=59.0), dict(name="f", img_s=5, accuracy=80.0)]
+    assert [r["name"] for r in S.pareto_front(rs)] == ["d", "b", "a"]
+    grid = S.candidate_grid(12)
+    assert grid[0] == ("dense", {}) and grid[1][0] == "README"
+    assert all(0 <= b < 12 and 0 < v["keep_ratio"] <= 1 for _, s in grid for b, v in s.items())
+    assert any(v.get("update") is False for _, s in grid for v in s.values())       # score-carry candidates are in the family
+    assert all(name != "README" for name, _ in S.candidate_grid(6))                 # needs blocks 7 and 8
+
+
+def test_greedy_search_respects_the_floor_and_prefers_cheap_accuracy():
+    """Synthetic evaluator: speed grows with the tokens removed (earlier blocks remove more work), accuracy falls by a
+    per-block price.  The search must never return a schedule below the floor, must prune the cheap blocks first, and
+    its history must be strictly faster at every step."""
+    from rajni_vit_b200 import schedule as S
+    depth, price = 6, {1: 8.0, 2: 0.5, 3: 0.4, 4: 6.0, 5: 0.2}
+
+    def fake(sched):
+        counts = S.token_counts(sched, depth, 101)
+        work = sum(counts)
+        loss = sum(price[b] * (1.0 - v["keep_ratio"]) * 10 for b, v in sched.items())
+        return {"img_s": 1e6 / work, "accuracy": 90.0 - loss}
+
+    sched, hist = S.greedy_search(fake, depth, floor=85.0, blocks=range(1, depth), ratios=(1.0, 0.9, 0.8, 0.7))
+    assert hist[0]["schedule"] == {} and len(hist) > 3
+    assert all(h["accuracy"] >= 85.0 for h in hist)
+    assert all(b["img_s"] > a["img_s"] for a, b in zip(hist, hist[1:]))
+    assert sched == hist[-1]["schedule"] and fake(sched)["accuracy"] >= 85.0
+    # the expensive blocks (1 and 4) stay dense; block 5 buys no speed in this evaluator (nothing runs after it), so it stays too
+    assert set(sched) == {2, 3} and sched[2]["keep_ratio"] == 0.7 and sched[3]["keep_ratio"] == 0.7
+    # nothing admissible: the dense model comes back
+    sched0, hist0 = S.greedy_search(fake, depth, floor=90.0, blocks=[1, 4])
+    assert sched0 == {} and len(hist0) == 1
