@@ -1,10 +1,9 @@
-"""Throughput / agreement sweep over pruning schedules (the reference leaves schedule choice to the user).
+"""Throughput / accuracy sweep over pruning schedules + greedy search (rajni_vit_b200.schedule).
 
-For every candidate schedule: images/s on this GPU, tensor work per image, and top-1 agreement + mean |dlogit| against the
-UN-PRUNED model on the same inputs (with real weights and labels, pass a loader to rajni_vit_b200.evaluate_model instead:
-agreement on random-init weights only says how much the pruning perturbs the logits).
+    python tools/schedule_sweep.py [--model vit_base_patch16_224] [--batch 256] [--batches 2] [--steps 10] [--floor 95] [--ckpt file]
 
-    python tools/schedule_sweep.py [--model vit_base_patch16_224] [--batch 256] [--steps 20]
+Accuracy axis: agreement with the UN-PRUNED model on synthetic images (random-init or --ckpt weights); with real data use
+rajni_vit_b200.schedule.sweep / search on batches of (images, labels) from the CLI's loader - the axis is then top-1.
 """
 import argparse
 import os
@@ -13,60 +12,40 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from rajni_vit_b200 import RAJNIViTWrapper  # noqa: E402
+from rajni_vit_b200 import load_checkpoint, schedule as S  # noqa: E402
 from rajni_vit_b200.vit import create_model  # noqa: E402
-
-
-def candidates(depth):
-    yield "none", {}
-    yield "README {3:.88,4:.88,7:.8,8:.72}", {3: {"keep_ratio": 0.88}, 4: {"keep_ratio": 0.88}, 7: {"keep_ratio": 0.8}, 8: {"keep_ratio": 0.72}}
-    for r in (0.9, 0.8, 0.7):
-        yield f"every block from 3, keep {r}", {i: {"keep_ratio": r} for i in range(3, depth)}
-    for r in (0.7, 0.5):
-        yield f"blocks 3,6,9 keep {r}", {i: {"keep_ratio": r} for i in (3, 6, 9) if i < depth}
-    yield "blocks 3,6,9 keep .7, scores carried", {3: {"keep_ratio": 0.7}, 6: {"keep_ratio": 0.7, "update": False}, 9: {"keep_ratio": 0.7, "update": False}}
-
-
-def flops_per_image(counts, C, hidden, P, classes=1000):
-    total = 2.0 * P * C * 768 + 2.0 * C * classes
-    for i, n in enumerate(counts):
-        np_ = counts[i + 1] if i + 1 < len(counts) else n      # tokens after this block's pruning (last block: unknown, unchanged)
-        total += 6.0 * n * C * C + 4.0 * np_ * np_ * C + 2.0 * np_ * C * C + 4.0 * np_ * C * hidden
-    return total
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="vit_base_patch16_224")
     ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--batches", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--floor", type=float, default=None, help="also run the greedy search with this accuracy floor (%%)")
+    ap.add_argument("--ckpt", default=None)
     args = ap.parse_args()
-    base = create_model(args.model, seed=0)
-    C, depth = base.patch_embed.proj.out_channels, len(base.blocks)
-    size = base.patch_embed.img_size[0]
-    x = torch.randn(args.batch, 3, size, size, generator=torch.Generator().manual_seed(1234)).cuda()
-    ref = None
-    print(f"{'schedule':42s} {'img/s':>9s} {'GFLOP/img':>10s} {'final tokens':>12s} {'top-1 agree':>11s} {'mean|dlogit|':>12s}")
-    for name, sched in candidates(depth):
-        m = RAJNIViTWrapper(create_model(args.model, seed=0), sched).cuda().eval()
-        y = m(x)
-        for _ in range(3):
-            m(x)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            m(x)
-        e1.record()
-        torch.cuda.synchronize()
-        ips = args.batch * args.steps / (e0.elapsed_time(e1) * 1e-3)
-        counts = m.get_last_stats()["token_counts"]
-        if ref is None:
-            ref = y
-        agree = (y.argmax(1) == ref.argmax(1)).float().mean().item()
-        dl = (y - ref).abs().mean().item()
-        gf = flops_per_image(counts, C, base.blocks[0].mlp.fc1.out_features, (size // 16) ** 2) / 1e9
-        print(f"{name:42s} {ips:9.0f} {gf:10.2f} {counts[-1]:12d} {agree:11.3f} {dl:12.4f}", flush=True)
-        del m
+
+    def make():
+        m = create_model(args.model, seed=0)
+        if args.ckpt:
+            load_checkpoint(args.ckpt, m)
+        return m
+
+    size = make().patch_embed.img_size[0]
+    g = torch.Generator().manual_seed(1234)
+    batches = [torch.randn(args.batch, 3, size, size, generator=g) for _ in range(args.batches)]
+    res = S.sweep(make, batches, timing_steps=args.steps)
+    print(f"{'schedule':48s} {'img/s':>9s} {'GFLOP/img':>10s} {'final tokens':>12s} {'accuracy %':>10s}")
+    for r in res:
+        print(f"{r['name']:48s} {r['img_s']:9.0f} {r['gflop_per_image']:10.2f} {r['token_counts'][-1]:12d} {r['accuracy']:10.2f}", flush=True)
+    print("Pareto front (fastest first):", [r["name"] for r in S.pareto_front(res)])
+    if args.floor is not None:
+        sched, hist = S.search(make, batches, floor=args.floor, timing_steps=max(3, args.steps // 2))
+        print(f"greedy search, accuracy >= {args.floor} %: {len(hist) - 1} accepted moves")
+        for h in hist:
+            print(f"  {h['img_s']:9.0f} img/s  {h['accuracy']:6.2f} %  {h['schedule']}")
+        print("schedule:", sched)
 
 
 if __name__ == "__main__":
