@@ -6,6 +6,8 @@
 // One CTA per SM loops over work units.  A unit fills the two 128-row score tiles of the SM:
 //   Np > 128 : one (image, head); tile 0 = queries 0..127, tile 1 = queries 128..Np-1, shared K/V
 //   Np <= 128: two (image, head) pairs, one per tile, each with its own K/V
+//   Np <= 64 : k = 2..8 consecutive images are PACKED into one tile (host side: launch_attention_tc); the softmax masks every
+//              row to the keys of its own image (kPacked)
 // Roles (512 threads):
 //   warps 0-3 / 4-7 : softmax + epilogue of tile 0 / tile 1 (thread = query row = TMEM lane)
 //   warp 8          : tcgen05.mma issuer (one lane), an event loop over the two tiles
@@ -55,6 +57,7 @@ struct AttnTcParams {
     const int32_t* row_map;
     __nv_bfloat16* out;
     int N_src, Np, Np_pad, C, H, BH, two_tiles, n_units;
+    int seg;                    // tokens per image inside a PACKED tile (several short images share a tile); == Np when not packed
     int o_col, o_outside;       // TMEM column of O inside a tile; o_outside = O does not overlap S's columns
     int split_col;              // > 0 (needs o_outside): P V starts once P's columns [0, split_col) are written, the rest follows
     int ksplit;                 // key column where attention_pipe.cu splits a row between its two exp warps (row-sum order)
@@ -95,6 +98,7 @@ __device__ __forceinline__ int unit_item(const AttnTcParams& p, int u, int t) {
     return p.reverse ? p.BH - 1 - item : item;
 }
 
+template <bool kPacked>
 __global__ void __launch_bounds__(kAtThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, const AttnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -358,23 +362,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             float sum = 1.f;
             if (warp_live) {
                 uint32_t va[32], vb[32];
+                // Key window of this row: all Np keys, or - packed tile: the rows are the tokens of Np / seg short images,
+                // S holds every image against every image - the seg keys of the row's own image (block-diagonal mask).
+                // [wlo, whi) is the union over the warp's rows (consecutive rows: lane 0 has the lowest window).
+                int lo = 0, hi = Np, wlo = 0, whi = Np;
+                if (kPacked) {
+                    lo = (min(q, Np - 1) / p.seg) * p.seg;
+                    hi = lo + p.seg;
+                    wlo = __shfl_sync(0xffffffffu, lo, 0);
+                    whi = __shfl_sync(0xffffffffu, hi, 31);
+                }
                 // ---- pass 1: row maximum, two 32-column loads in flight per wait
                 float mx = -INFINITY;
                 auto max32 = [&](const uint32_t (&cur)[32], int c0) {
-                    if (c0 + 32 <= Np) {
+                    if (c0 >= lo && c0 + 32 <= hi) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) mx = fmax3(mx, __uint_as_float(cur[j]), __uint_as_float(cur[j + 1]));
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (c0 + j < Np) mx = fmaxf(mx, __uint_as_float(cur[j]));
+                        for (int j = 0; j < 32; ++j) if (c0 + j >= lo && c0 + j < hi) mx = fmaxf(mx, __uint_as_float(cur[j]));
                     }
                 };
-                for (int c0 = 0; c0 < Np; c0 += 64) {
+                for (int c0 = wlo & ~63; c0 < whi; c0 += 64) {
                     tmem_ld32(trow + c0, va);
-                    if (c0 + 32 < Np) tmem_ld32(trow + c0 + 32, vb);
+                    if (c0 + 32 < whi) tmem_ld32(trow + c0 + 32, vb);
                     tmem_ld_wait();
                     max32(va, c0);
-                    if (c0 + 32 < Np) max32(vb, c0 + 32);
+                    if (c0 + 32 < whi) max32(vb, c0 + 32);
                 }
                 if ((tid & 127) == 0) AT_TRACE(n, 13 + 8 * t);
                 // ---- pass 2: p = exp2((s - max) * scale * log2 e), row sum, bf16 P back into TMEM.
@@ -400,12 +414,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
                     float e[32];
                     if (Np_pad - c0 >= 32) {
                         uint32_t pk[16];
-                        if (c0 + 32 <= Np) {
+                        if (c0 >= lo && c0 + 32 <= hi) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) e[j] = ex2_approx(fmaf(__uint_as_float(cur[j]), sl2, -mb));
+                        } else if (kPacked && (c0 + 32 <= wlo || c0 >= whi)) {   // no row of this warp has keys here (packed tile): P = 0
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) e[j] = 0.f;
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) e[j] = (c0 + j < Np) ? ex2_approx(fmaf(__uint_as_float(cur[j]), sl2, -mb)) : 0.f;
+                            for (int j = 0; j < 32; ++j) e[j] = (c0 + j >= lo && c0 + j < hi) ? ex2_approx(fmaf(__uint_as_float(cur[j]), sl2, -mb)) : 0.f;
                         }
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) pk[j >> 1] = float2_to_bf16x2(e[j], e[j + 1]);
@@ -415,7 +432,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
                     } else {                                                   // 16-column tail
                         uint32_t pk[8];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) e[j] = (c0 + j < Np) ? ex2_approx(fmaf(__uint_as_float(cur[j]), sl2, -mb)) : 0.f;
+                        for (int j = 0; j < 16; ++j) e[j] = (c0 + j >= lo && c0 + j < hi) ? ex2_approx(fmaf(__uint_as_float(cur[j]), sl2, -mb)) : 0.f;
 #pragma unroll
                         for (int j = 0; j < 16; j += 2) pk[j >> 1] = float2_to_bf16x2(e[j], e[j + 1]);
                         add16(e, 0, c0 < ksplit);
@@ -516,7 +533,21 @@ static int at_num_sms() {
 int launch_attention_tc(const void* qkv, const int32_t* row_map, void* out, int B, int N_src, int Np,
                         int C, int H, float scale, int reverse, cudaStream_t stream) {
     if (Np > 256) return 0;
+    // Short images share a tile: k consecutive images (k divides B, k * Np <= 128) are presented to the kernel as ONE image
+    // of k * Np tokens - their rows are consecutive in qkv, in row_map and in out, so only the view changes - and the softmax
+    // masks every row to the seg = Np keys of its own image.  A tile costs ~2 us whatever it holds (the chain S -> softmax ->
+    // P V -> O is latency-bound), so vit_large's 14..64-token blocks run k = 2..8 times fewer of them.  The images of a tile
+    // share one P V product: P is exactly 0 outside the row's image, so finite inputs give the same result as separate tiles
+    // (up to the order of the fp32 accumulation), but a NaN/Inf value row reaches the images packed with it (0 * NaN).
+    int seg = Np;
+    static const bool nopack = getenv("RAJNI_ATTN_NOPACK") != nullptr;
+    if (!nopack && Np <= 64) {
+        int k = 128 / Np;
+        while (k > 1 && B % k) --k;
+        if (k > 1) { B /= k; N_src *= k; Np *= k; }
+    }
     AttnTcParams p{};
+    p.seg = seg;
     p.qkv = static_cast<const __nv_bfloat16*>(qkv);
     p.row_map = row_map;
     p.out = static_cast<__nv_bfloat16*>(out);
@@ -545,17 +576,19 @@ int launch_attention_tc(const void* qkv, const int32_t* row_map, void* out, int 
     CUtensorMap tmap_out;
     RAJNI_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15u) == 0, RAJNI_EINVAL, "attention_tc: out must be 16-byte aligned (TMA store)");
     if (int rc = make_tmap_bf16_3d_box(&tmap_out, out, B, Np, C, 32)) return rc;
-    static int attr_smem_dev[kMaxDevices] = {};
-    int& attr_smem = attr_smem_dev[current_device()];
+    const bool packed = seg < Np;
+    auto kern = packed ? attention_tc_kernel<true> : attention_tc_kernel<false>;
+    static int attr_smem_dev[2][kMaxDevices] = {};
+    int& attr_smem = attr_smem_dev[packed][current_device()];
     if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         RAJNI_REQUIRE(e == cudaSuccess, RAJNI_ECUDA, "attention_tc: smem attribute (%d B): %s", smem, cudaGetErrorString(e));
         attr_smem = smem;
     }
     int grid = p.n_units < at_num_sms() ? p.n_units : at_num_sms();
     static const int cta_cap = getenv("RAJNI_ATTN_MAX_CTAS") ? atoi(getenv("RAJNI_ATTN_MAX_CTAS")) : 0;      // experiments: share the GPU
     if (cta_cap > 0 && grid > cta_cap) grid = cta_cap;
-    cudaError_t le = launch_kernel(attention_tc_kernel, dim3(grid), dim3(kAtThreads), (size_t)smem, stream, 1, tmap, tmap_out, p);
+    cudaError_t le = launch_kernel(kern, dim3(grid), dim3(kAtThreads), (size_t)smem, stream, 1, tmap, tmap_out, p);
     count_launch();
     RAJNI_REQUIRE(le == cudaSuccess, RAJNI_ECUDA, "attention_tc: launch failed: %s", cudaGetErrorString(le));
     int rc = check_launch("attention_tc");
