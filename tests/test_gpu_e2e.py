@@ -149,7 +149,7 @@ def near_tie_mismatch(ours: torch.Tensor, ref_scores: torch.Tensor, keep: int, r
     k-th score: bf16 activations perturb the scores by O(1e-2) relative, and random-init scores are
     nearly flat, so tokens that close to the cut can swap."""
     B = ours.shape[0]
-    worst, overlap = 0.0, 0.0
+    worst, overlap, in_band, cands = 0.0, 0.0, 0, 0
     for b in range(B):
         s = ref_scores[b, 1:].double()
         cut = torch.sort(s, descending=True).values[keep - 1].item()
@@ -158,6 +158,9 @@ def near_tie_mismatch(ours: torch.Tensor, ref_scores: torch.Tensor, keep: int, r
         overlap += len(ref_set & our_set) / keep
         for t in ref_set ^ our_set:
             worst = max(worst, abs(s[t - 1].item() - cut) / abs(cut))
+        in_band += int(((s - cut).abs() <= rel_gap * abs(cut)).sum())
+        cands += s.numel()
+    near_tie_mismatch.band_fraction = in_band / max(cands, 1)      # how much of the candidate set the exemption covers
     return overlap / B, worst
 
 
@@ -203,6 +206,10 @@ def test_forward_vs_oracle_full_models(pkg, name, sched, batch, size):
         ov, worst = near_tie_mismatch(kidx, rec["scores"], keep, 0.03)
         print(f"  block {rec['block']}: kept-set overlap {ov:.4f}, worst disagreeing token is {worst:.2e} (relative) from the cut")
         assert worst < 0.03
+        # the exemption must stay an exemption: few candidates sit in the band, and almost every kept token agrees
+        # (measured on 256 images in bench.py's parity sample: 2.8 % of the candidates in the band, 0.28 % of the kept tokens differ)
+        # (with fewer than 64 candidates per image one token is already > 1.5 % of them: only the overlap is bounded there)
+        assert ov > 0.97 and (near_tie_mismatch.band_fraction < 0.12 or rec["scores"].shape[1] <= 64), (near_tie_mismatch.band_fraction, ov)
     free, _ = orc.forward(params, images, sched)
     print(f"{name} (free-running): max |dlogit| {(logits - free).abs().max().item():.4f}, "
           f"top-1 agreement {(logits.argmax(1) == free.argmax(1)).float().mean().item():.3f}")
