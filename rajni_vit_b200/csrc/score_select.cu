@@ -316,9 +316,10 @@ __device__ void select_rank_emit(const float* score, uint32_t* key, uint32_t* s_
     for (int i = tid; i < 256; i += NT) s_cnt[i] = 0;
     tail_sync<NT>();
     const int n = tid;                                   // N <= 256 <= NT
-    const uint32_t kn = (n >= 1 && n < N) ? key[n] : 0xffffffffu;
+    const bool live = n >= 1 && n < N;
+    const uint32_t kn = live ? key[n] : 0xffffffffu;
     int gt = 0;
-    {
+    if ((n & ~31) < N) {                                 // warps past the last token have nothing to count
         const uint4* k4 = reinterpret_cast<const uint4*>(key);
 #pragma unroll 4
         for (int m = 0; m < N4 / 4; ++m) {
@@ -326,7 +327,7 @@ __device__ void select_rank_emit(const float* score, uint32_t* key, uint32_t* s_
             gt += (k.x > kn) + (k.y > kn) + (k.z > kn) + (k.w > kn);
         }
     }
-    if (n >= 1 && n < N) atomicAdd(&s_cnt[gt], 1u);      // gt <= N - 2 <= 254
+    if (live) atomicAdd(&s_cnt[gt], 1u);                 // gt <= N - 2 <= 254
     tail_sync<NT>();
     bool take = false;
     if (n == 0) {
