@@ -134,7 +134,10 @@ int rajni_gemm_row_stats_slots(int N);
  * qkv [B,N_src,3C] bf16; when row_map != NULL token j of image b is read from
  * global row row_map[b*Np+j] (gather fused into the loads), else N_src == Np.
  * out [B,Np,C] bf16 = softmax(q k^T * scale) v, heads concatenated. D must be 64.
- * reverse != 0: process the images last-to-first (L2 reuse hint, see RAJNI_HINT_REVERSE_M). */
+ * reverse != 0: process the images last-to-first (L2 reuse hint, see RAJNI_HINT_REVERSE_M).
+ * Images are independent for finite inputs.  Np > 64: also for non-finite ones (a NaN/Inf in one image never reaches
+ * another's output).  Np <= 64: consecutive images may share a tile and one P V product (masked softmax): a NaN/Inf VALUE row
+ * then reaches the images packed with it (0 * NaN); the environment variable RAJNI_ATTN_NOPACK=1 keeps one image per tile. */
 int rajni_attention_fwd(const void* qkv, const int32_t* row_map, void* out,
                         int B, int N_src, int Np, int C, int H, float scale, int reverse, void* stream);
 /* The same call with the kernel chosen by the caller (tests and A/B timing; results agree within bf16 rounding):

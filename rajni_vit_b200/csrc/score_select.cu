@@ -234,27 +234,16 @@ __device__ __forceinline__ void score_row_load(const __nv_bfloat16* row, int lan
     }
 }
 
-// The CLS query sits in registers (q, pre-scaled floats) or as the raw bf16 row in shared memory (qs; unpacked and scaled by
-// 1/8 on the fly: the same values).
-template <int CPL, bool kQShared>
-__device__ __forceinline__ void score_row_math(const uint4 (&kk)[CPL], const uint4 (&vv)[CPL], const float (&q)[CPL][8], const uint4* qs,
-                                               int lane, int chunks, int C, int H, int N, int n, float* logit_dst, float* vm_dst,
-                                               int vm_stride, float inv_h) {
+template <int CPL>
+__device__ __forceinline__ void score_row_math(const uint4 (&kk)[CPL], const uint4 (&vv)[CPL], const float (&q)[CPL][8],
+                                               int lane, int H, int N, int n, float* logit_dst, float* vm_dst, int vm_stride, float inv_h) {
     float va[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < CPL; ++i) {
         float2 k0 = bf16x2_to_float2(kk[i].x), k1 = bf16x2_to_float2(kk[i].y);
         float2 k2 = bf16x2_to_float2(kk[i].z), k3 = bf16x2_to_float2(kk[i].w);
-        float4 qa, qb;
-        if (kQShared) {
-            const uint4 u = qs[min(lane + 32 * i, chunks - 1)];
-            const float2 a = bf16x2_to_float2(u.x), bb = bf16x2_to_float2(u.y), c = bf16x2_to_float2(u.z), d = bf16x2_to_float2(u.w);
-            qa = make_float4(a.x * 0.125f, a.y * 0.125f, bb.x * 0.125f, bb.y * 0.125f);
-            qb = make_float4(c.x * 0.125f, c.y * 0.125f, d.x * 0.125f, d.y * 0.125f);
-        } else {
-            qa = make_float4(q[i][0], q[i][1], q[i][2], q[i][3]);
-            qb = make_float4(q[i][4], q[i][5], q[i][6], q[i][7]);
-        }
+        const float4 qa = make_float4(q[i][0], q[i][1], q[i][2], q[i][3]);
+        const float4 qb = make_float4(q[i][4], q[i][5], q[i][6], q[i][7]);
         float dot = qa.x * k0.x;
         dot = fmaf(qa.y, k0.y, dot); dot = fmaf(qa.z, k1.x, dot); dot = fmaf(qa.w, k1.y, dot);
         dot = fmaf(qb.x, k2.x, dot); dot = fmaf(qb.y, k2.y, dot); dot = fmaf(qb.z, k3.x, dot);
@@ -288,7 +277,7 @@ __device__ __forceinline__ void score_row(const __nv_bfloat16* row, const float 
                                           int C, int H, int N, int n, float* logit_dst, float* vm_dst, int vm_stride, float inv_h) {
     uint4 kk[CPL], vv[CPL];
     score_row_load<CPL>(row, lane, chunks, C, true, kk, vv);
-    score_row_math<CPL, false>(kk, vv, q, nullptr, lane, chunks, C, H, N, n, logit_dst, vm_dst, vm_stride, inv_h);
+    score_row_math<CPL>(kk, vv, q, lane, H, N, n, logit_dst, vm_dst, vm_stride, inv_h);
 }
 
 // CLS query of the image, pre-scaled by 1/sqrt(64) (exact: power of two)
@@ -359,32 +348,27 @@ __device__ __forceinline__ void select_any(const SelSmem& sm, const ScoreSelectP
     else select_and_emit<NT>(sm.score, sm.hist, sm.misc, sm.warp_off, p, b);
 }
 
-// squared distance of one value row from mu; four interleaved partial sums, the same order whether the row is read from
-// shared memory or (16-byte loads past L1) from the scratch other CTAs of the launch wrote
-template <bool kVmGlobal>
+// squared distance of one value row (shared memory) from mu; four interleaved partial sums
 __device__ __forceinline__ float row_dist2(const float* row, const float* mu) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int i = 0; i < kHeadDim / 4; ++i) {
-        float4 v;
-        if (kVmGlobal) v = __ldcg(reinterpret_cast<const float4*>(row) + i);
-        else v = make_float4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
+        const float4 v = make_float4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
         const float d0 = v.x - mu[4 * i], d1 = v.y - mu[4 * i + 1], d2 = v.z - mu[4 * i + 2], d3 = v.w - mu[4 * i + 3];
         a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1); a2 = fmaf(d2, d2, a2); a3 = fmaf(d3, d3, a3);
     }
     return (a0 + a1) + (a2 + a3);
 }
 
-// The per-image tail: statistics of the value rows and the CLS logits, scores, selection.  The NT threads that run it (the
-// CTA's 512, or the 448 of the overlapped kernel's compute warps: same bits, see block_sum) call it after a barrier that made
-// sm.logit (shared) and vm complete:
-// rows of `vs` floats in shared memory, or - long sequences in the overlapped kernel - the global scratch written by other
-// CTAs of the launch (read past L1).  Thread-per-token wherever the reference's reductions allow: ~9 block barriers in all.
-template <int NT, bool kVmGlobal>
+// The per-image tail: statistics of the value rows and the CLS logits, scores, selection.  The CTA's NT threads call it after a
+// barrier that made sm.logit and vm (rows of kVmSmemStride floats, both in shared memory) complete.  Thread-per-token wherever
+// the reference's reductions allow: ~9 block barriers in all.  (NT and the 512 "virtual threads" of block_sum: the overlapped
+// kernel of tools/probes/score_overlap_persistent_experiment.patch runs the same tail on 448 threads with the same bits.)
+template <int NT>
 __device__ void score_tail(const SelSmem& sm, const float* vm, const ScoreSelectParams& p, int b, int trace_row = 0) {
     const int N = p.N, H = p.H;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int vs = kVmGlobal ? kHeadDim : kVmSmemStride;
+    const int vs = kVmSmemStride;
     const float inv_h = 1.0f / (float)H;
     SC_TRACE(32 + trace_row, 4);
     // ---- mean over tokens of the head-averaged value (importance.py:25): 8 interleaved partial sums per dim, then their sum
@@ -393,14 +377,7 @@ __device__ void score_tail(const SelSmem& sm, const float* vm, const ScoreSelect
         for (int g = tid >> 6; g < kSelThreads / 64; g += NT / 64) {
             float acc = 0.f;
             int n = g;
-            for (; n + 24 < N; n += 32) {            // four rows in flight (the global reads are L2 round trips)
-                const float x0 = kVmGlobal ? __ldcg(vm + (size_t)n * vs + d) : vm[(size_t)n * vs + d];
-                const float x1 = kVmGlobal ? __ldcg(vm + (size_t)(n + 8) * vs + d) : vm[(size_t)(n + 8) * vs + d];
-                const float x2 = kVmGlobal ? __ldcg(vm + (size_t)(n + 16) * vs + d) : vm[(size_t)(n + 16) * vs + d];
-                const float x3 = kVmGlobal ? __ldcg(vm + (size_t)(n + 24) * vs + d) : vm[(size_t)(n + 24) * vs + d];
-                acc += x0; acc += x1; acc += x2; acc += x3;
-            }
-            for (; n < N; n += 8) acc += kVmGlobal ? __ldcg(vm + (size_t)n * vs + d) : vm[(size_t)n * vs + d];
+            for (; n < N; n += 8) acc += vm[(size_t)n * vs + d];
             sm.scratch[g * 64 + d] = acc;
         }
         tail_sync<NT>();
@@ -414,7 +391,7 @@ __device__ void score_tail(const SelSmem& sm, const float* vm, const ScoreSelect
     }
     SC_TRACE(32 + trace_row, 5);
     // ---- r[n] = || vm[n] - mu ||  (importance.py:27): thread per token
-    for (int n = tid; n < N; n += NT) sm.r[n] = sqrtf(row_dist2<kVmGlobal>(vm + (size_t)n * vs, sm.mu));
+    for (int n = tid; n < N; n += NT) sm.r[n] = sqrtf(row_dist2(vm + (size_t)n * vs, sm.mu));
     SC_TRACE(32 + trace_row, 6);
     // ---- per-head softmax statistics over all N tokens (importance.py:20): warp per head
     for (int h = warp; h < H; h += NT / 32) {
@@ -501,7 +478,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) score_select_kernel(const Scor
                 score_row<CPL>(img + (size_t)n * 3 * C, q, lane, chunks, C, H, N, n, sm.logit, s_vm, kVmSmemStride, 1.0f / (float)H);
         }
         __syncthreads();
-        score_tail<kSelThreads, false>(sm, s_vm, p, b);
+        score_tail<kSelThreads>(sm, s_vm, p, b);
     } else {
         for (int n = tid; n < N; n += kSelThreads) sm.score[n] = p.scores_in[(size_t)b * N + n];
         __syncthreads();

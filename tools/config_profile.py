@@ -14,10 +14,12 @@ CASES = [("C2", "vit_base_patch16_224", README, 256, 224),
          ("C3", "vit_small_patch16_224", {i: {"keep_ratio": 0.7} for i in range(3, 12)}, 512, 224),
          ("C4", "vit_large_patch16_224", {i: {"keep_ratio": 0.9} for i in range(24)}, 256, 224),
          ("C5", "deit_base_patch16_384", README, 128, 384)]
-only = sys.argv[1:]
+# config_profile.py C4 C5 ...      full global batch;   config_profile.py C4/8 ...   the batch of one of 8 shards
+only = {a.split("/")[0]: int(a.split("/")[1]) if "/" in a else 1 for a in sys.argv[1:]}
 for name, model_name, sched, B, S in CASES:
     if only and name not in only:
         continue
+    B //= only.get(name, 1)
     m = RAJNIViTWrapper(create_model(model_name, seed=0), sched).cuda().eval()
     m.use_cuda_graph = False
     x = torch.randn(B, 3, S, S, device="cuda")
