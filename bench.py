@@ -97,6 +97,15 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
 
+    def start_ready(self, timeout=5.0):
+        """start(), then wait for the first sample: forking nvidia-smi and its driver attach take tens of ms during which
+        kernel launches can stall - that must happen BEFORE the timed region, not inside it.  Samples taken so far are dropped."""
+        self.start()
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
+        self.rows.clear()
+
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -363,12 +372,14 @@ def main():
         return float(ms.item())
 
     # ---------------- device-resident throughput ----------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start_ready()                              # nvidia-smi is attached and polling before the warm-up ends
     for i in range(args.warmup):
         model(resident[i & 1])
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.rows.clear()                               # keep only the samples of the timed region
     launches0 = _lib.launch_count()
     last = {}
 
@@ -389,7 +400,7 @@ def main():
     sus_steps = max(args.steps, int(math.ceil(1200.0 / (ms_total / args.steps))))
     sampler2 = ClockSampler(local)
     if rank == 0:
-        sampler2.start()
+        sampler2.start_ready()
     sus_ms = timed(step, sus_steps)
     sus_clocks = sampler2.stop() if rank == 0 else None
     sustained = {"value": round(world * B * sus_steps / (sus_ms * 1e-3), 1), "unit": "images/s", "steps": sus_steps,

@@ -229,6 +229,33 @@ def test_full_batch_properties(pkg):
     assert torch.equal(sub, y[64:96])
 
 
+def test_stream_k_option_matches_default_within_rounding(pkg):
+    """wrapper.stream_k (opt-in): at 32 images the fc2 GEMMs of the 197-token blocks (75 tiles on 74 CTA pairs) split their
+    leftover tile along K.  Same products, fp32 sums in another order: logits agree within the bf16 drift of a forward, the
+    token counts are equal, the kept sets differ only where a score tie straddles the cut."""
+    from rajni_vit_b200 import ops
+    assert ops.stream_k_plan(32 * 197, 768, 3072, ops.EPI_BIAS | ops.EPI_RESIDUAL | ops.EPI_ROW_STATS)[0] > 0
+    model = build(pkg, "vit_base_patch16_224", README_SCHEDULE)
+    images = make_images(32, 224, 77).cuda()
+    assert model.stream_k is False
+    y0 = model(images)
+    keep0 = [k.clone() if k is not None else None for k in model._last_keep_idx]
+    model.stream_k = True
+    y1 = model(images)
+    y1b = model(images)
+    assert torch.equal(y1, y1b)                                   # deterministic
+    assert model.get_last_stats()["token_counts"] == [197, 197, 197, 197, 173, 152, 152, 152, 121, 87, 87, 87]
+    d = (y1 - y0).abs().max().item()
+    print("stream-K vs default: max |dlogit|", d, "logit std", y0.std().item())
+    assert d < 0.08
+    for a, b in zip(keep0, model._last_keep_idx):
+        if a is not None:
+            ov = np.mean([len(set(r0.tolist()) & set(r1.tolist())) / len(r0) for r0, r1 in zip(a.cpu().numpy(), b.cpu().numpy())])
+            assert ov > 0.97, ov
+    model.stream_k = False
+    assert torch.equal(model(images), y0)                         # and back: the default path is untouched
+
+
 def test_evaluate_model(pkg):
     model = build(pkg, "vit_micro_patch16_64", MICRO_SCHEDULE)
     g = torch.Generator().manual_seed(0)
