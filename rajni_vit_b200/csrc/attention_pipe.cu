@@ -18,8 +18,13 @@
 //   warps 13-15 LOAD   dense call: one thread, three TMA boxes per item (3-d map: rows past the image are ZERO-filled, so
 //                      one image's Inf/NaN can never reach another's output); gathered call: cp.async row gather by row_map
 //
-// TMEM (512 columns): nbuf score buffers of s_stride columns (2 at Np_pad 208 ... 4 at Np_pad <= 96), then one or two
+// TMEM (512 columns): nbuf score buffers of s_stride columns (2 at Np_pad 208 ... 3 at Np_pad <= 128), then one or two
 // 64-column O buffers: S(g+1) is computed while the exp warps work on tile g and P(g-1) V runs.
+//
+// One-tile items of at most 112 keys run the exp warps in FULL-ROW mode (ap_exp_full): a thread holds its whole row of S, so
+// no maximum is exchanged, and warps 0-3 take the even tiles, warps 4-7 the odd ones - the two exp warps of a scheduler are
+// half a period apart, one's TMEM wait / maximum / P store under the other's exponentials (dense 87 tokens: 30.8 us against
+// 43.5 us for attention_tc; gathered calls stay with attention_tc's seven loader warps).
 #include <cuda.h>
 
 #include <type_traits>
@@ -68,6 +73,7 @@ struct AttnPipeParams {
     int N_src, Np, Np_pad, C, H, BH, tpi;      // tpi = 128-row tiles per (image, head) item
     int nbuf, s_stride, n_obuf, o_col;         // score buffer b at column b*s_stride; O buffer ob at o_col + 64*ob
     int split;                                  // key columns [0, split) -> exp warps 0-3, [split, Np_pad) -> warps 4-7
+    int fullrow;                                // one-tile items of <= 112 keys: a thread takes its WHOLE row, warps 0-3 the even tiles, 4-7 the odd ones
     int plane_bytes, stages, reverse;
     int dbg;                                    // experiments (tools/probes, RAJNI_ATTN_TRACE builds only): skip parts of the work
     float scale_log2;
@@ -217,6 +223,49 @@ __device__ __forceinline__ float ap_exp_half(uint32_t sb, int cb, uint32_t pcol,
     return sum0 + sum1;
 }
 
+// Full-row variant for one-tile items of at most 112 keys (K16 = Np_pad / 16): the thread holds its whole row of S, so
+// there is no second half to exchange a maximum with, and the two exp warps of a scheduler work on DIFFERENT tiles (even /
+// odd): one warp's TMEM wait, maximum and P store run under the other's exponentials instead of both marching in step.
+// The row sum is still taken in two parts, [0, SPLIT) and [SPLIT, NCOL) with SPLIT as in the two-half scheme, each with
+// its even / odd column chains, so the result has the same bits as ap_exp_half's (and attention_tc's).
+template <int K16>
+__device__ __forceinline__ void ap_exp_full(uint32_t sb, uint32_t pcol, int Np, float sl2, uint64_t* taken_bar, int lane,
+                                            float& sum_a, float& sum_b) {
+    constexpr int NCOL = 16 * K16, N32 = NCOL / 32, HAS16 = K16 & 1;
+    constexpr int SPLIT = ((NCOL / 2) + 15) & ~15;
+    uint32_t s[NCOL];
+#pragma unroll
+    for (int i = 0; i < N32; ++i) tmem_ld32(sb + 32 * i, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * i]));
+    if (HAS16) tmem_ld16(sb + 32 * N32, *reinterpret_cast<uint32_t(*)[16]>(&s[32 * N32]));
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(taken_bar);
+    if (NCOL > Np) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (NCOL - 16 + i >= Np) s[NCOL - 16 + i] = 0xff800000u;      // -inf
+    }
+    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < NCOL; i += 2) m4[(i >> 1) & 3] = ap_fmax3(m4[(i >> 1) & 3], __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+    const float mb = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sl2;
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCOL; j += 2) {
+        if (j == SPLIT) { sum_a = sum0 + sum1; sum0 = 0.f; sum1 = 0.f; }
+        const float e0 = ap_ex2(fmaf(__uint_as_float(s[j]), sl2, -mb)), e1 = ap_ex2(fmaf(__uint_as_float(s[j + 1]), sl2, -mb));
+        sum0 += e0;
+        sum1 += e1;
+        s[j >> 1] = float2_to_bf16x2(e0, e1);
+    }
+    if (SPLIT < NCOL) sum_b = sum0 + sum1;
+    else { sum_a = sum0 + sum1; sum_b = 0.f; }
+    constexpr int W = NCOL / 2;                                               // 32-bit words of P
+    if (W & 32) tmem_st32(pcol, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+    if (W & 16) tmem_st16(pcol + (W & 32), *reinterpret_cast<uint32_t(*)[16]>(&s[W & 32]));
+    if (W & 8) tmem_st8(pcol + (W & 48), *reinterpret_cast<uint32_t(*)[8]>(&s[W & 48]));
+}
+
 __global__ void __launch_bounds__(kApThreads, 1)
 attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, const AttnPipeParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -252,8 +301,8 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
             }
             for (int i = 0; i < kApMaxBufs; ++i) {
                 mbar_init(&s_full[i], 1);
-                mbar_init(&p_full[i], 8);            // one arrival per exp warp
-                mbar_init(&s_taken[i], 8);
+                mbar_init(&p_full[i], p.fullrow ? 4 : 8);            // one arrival per exp warp (of the tile's parity)
+                mbar_init(&s_taken[i], p.fullrow ? 4 : 8);
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&o_full[i], 1);
@@ -479,6 +528,39 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
         const float sl2 = p.scale_log2;
         ApCursor c;
         int slot = 0;
+        if (p.fullrow) {
+            // one-tile items, whole rows: this warp takes the tiles of its parity only (see ap_exp_full)
+            const int k16 = Np_pad >> 4;
+            for (; c.g < G; c.advance(p)) {
+                if ((c.g & 1) == half) {
+                    mbar_wait(&s_full[c.buf], c.buf_ph);
+                    if (q * 32 < Np) {
+                        tc_fence_after();
+                        const uint32_t sb = lane_base + c.buf * p.s_stride;
+                        float sa = 0.f, sbm = 0.f;
+                        switch (k16) {                                        // warp-uniform: one straight-line body per width
+                            case 7: ap_exp_full<7>(sb, sb, Np, sl2, &s_taken[c.buf], lane, sa, sbm); break;
+                            case 6: ap_exp_full<6>(sb, sb, Np, sl2, &s_taken[c.buf], lane, sa, sbm); break;
+                            case 5: ap_exp_full<5>(sb, sb, Np, sl2, &s_taken[c.buf], lane, sa, sbm); break;
+                            case 4: ap_exp_full<4>(sb, sb, Np, sl2, &s_taken[c.buf], lane, sa, sbm); break;
+                            case 3: ap_exp_full<3>(sb, sb, Np, sl2, &s_taken[c.buf], lane, sa, sbm); break;
+                            case 2: ap_exp_full<2>(sb, sb, Np, sl2, &s_taken[c.buf], lane, sa, sbm); break;
+                            default: ap_exp_full<1>(sb, sb, Np, sl2, &s_taken[c.buf], lane, sa, sbm); break;
+                        }
+                        sums[(slot * 2 + 0) * 128 + row] = sa;
+                        sums[(slot * 2 + 1) * 128 + row] = sbm;
+                        tmem_st_wait();
+                        tc_fence_before();
+                    } else {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&s_taken[c.buf]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p_full[c.buf]);
+                }
+                if (++slot == kApSumSlots) slot = 0;
+            }
+        } else
         for (; c.g < G; c.advance(p)) {
             mbar_wait(&s_full[c.buf], c.buf_ph);
             if (warp == 0 && lane == 0) AP_TRACE(c.g, 8);
@@ -563,10 +645,16 @@ int launch_attention_pipe(const void* qkv, const int32_t* row_map, void* out, in
     p.nbuf = (512 - 64 * p.n_obuf) / p.s_stride;
     if (p.nbuf > kApMaxBufs) p.nbuf = kApMaxBufs;
     p.o_col = 512 - 64 * p.n_obuf;
-    p.split = ((Np_pad / 2) + 15) & ~15;
+    p.fullrow = (p.tpi == 1 && Np_pad <= 112) ? 1 : 0;
+    p.split = p.fullrow ? Np_pad : ((Np_pad / 2) + 15) & ~15;
     p.plane_bytes = (Np_pad * 128 + 1023) & ~1023;
     p.stages = kApSmemBudget / (3 * p.plane_bytes);
     if (p.stages > kApMaxStages) p.stages = kApMaxStages;
+    // One-tile items: S(g + nbuf) needs the Q/K of item g + nbuf while P V(g) still holds item g's stage, i.e. nbuf + 1 items in
+    // flight.  With as many score buffers as stages the (blocking, fixed-order) issuer would sit out a whole load latency per
+    // tile waiting for a stage that P V(g) has yet to release: 96-key items ran 46.6 us with 4 buffers, slower than 112-key ones
+    // with 3 (34.5 us).
+    if (p.tpi == 1 && p.nbuf > p.stages - 1) p.nbuf = p.stages - 1;
     RAJNI_REQUIRE(p.stages >= 2 && p.nbuf >= 2, RAJNI_EINVAL, "attention_pipe: Np=%d leaves %d stage(s), %d score buffer(s)", Np, p.stages, p.nbuf);
     // the last stage's Q operand of tile 1 is read 128 rows deep from row 128: keep that inside the allocation
     const int smem = p.stages * 3 * p.plane_bytes + kApOutStage + kApAuxBytes + kApBarBytes + 1024;

@@ -1,2 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -k "score or select or importance" > gpurun_out/cl_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/cl_tests.log
-timeout 300 python tools/score_small_bench.py > gpurun_out/score_small_cluster.txt 2>&1; cat gpurun_out/score_small_cluster.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2e_tests.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/r2e_tests.log
+python bench.py > gpurun_out/r2e_bench.json 2> gpurun_out/r2e_bench.err; echo "bench rc=$?"
+python tools/kbench.py > gpurun_out/r2e_kbench.log 2>&1; echo "kbench rc=$?"; grep attention gpurun_out/r2e_kbench.log
+timeout 300 python tools/config_profile.py C1 C3 > gpurun_out/r2e_config_profile.txt 2>&1; grep -E "bs|attention" gpurun_out/r2e_config_profile.txt
