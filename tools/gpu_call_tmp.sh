@@ -1,4 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2e_tests.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/r2e_tests.log
-python bench.py > gpurun_out/r2e_bench.json 2> gpurun_out/r2e_bench.err; echo "bench rc=$?"
-python tools/kbench.py > gpurun_out/r2e_kbench.log 2>&1; echo "kbench rc=$?"; grep attention gpurun_out/r2e_kbench.log
-timeout 300 python tools/config_profile.py C1 C3 > gpurun_out/r2e_config_profile.txt 2>&1; grep -E "bs|attention" gpurun_out/r2e_config_profile.txt
+cd tools/probes && nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I../../rajni_vit_b200/csrc gather4_rate_probe.cu -o /tmp/gather4_rate_probe -lcuda 2>/dev/null; cd ../..
+timeout 60 /tmp/gather4_rate_probe > gpurun_out/gather4_rate_probe.txt 2>&1; echo "rc=$?"; cat gpurun_out/gather4_rate_probe.txt
