@@ -1,3 +1,3 @@
-timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -k "attention" > gpurun_out/wi_tests.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/wi_tests.log
-timeout 300 python tools/attn_ab.py 121:87 152:121 100:70 197:173 > gpurun_out/attn_ab_warpitems.txt 2>&1; cat gpurun_out/attn_ab_warpitems.txt
-timeout 300 python tools/attn_ab.py 256 16 143:128 128:115 92:82 > gpurun_out/attn_ab_warpitems_c4.txt 2>&1; cat gpurun_out/attn_ab_warpitems_c4.txt
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2g_bench_2gpu.json 2> gpurun_out/r2g_bench_2gpu.err; echo "rc=$?"
+tail -c 300 gpurun_out/r2g_bench_2gpu.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/r2g_bench_ref_2gpu.json 2> gpurun_out/r2g_bench_ref_2gpu.err; echo "ref rc=$?"
