@@ -1,13 +1,16 @@
 // a4: C-ABI entry of the attention over kept tokens (attention.py:42-54) and its dispatch to the three tcgen05 kernels.
 //
-//   128 < Np, Np_pad <= 224, >= 6 (image, head) items per SM : attention_pipe.cu  (role-pipelined: exp / epilogue / MMA / load
-//                                    warps, S multi-buffered in TMEM, half rows of S held in registers): 1.2-1.26x the kernel below
-//                                    at 152..197 tokens and batch 256 (profiles/r2_attention_pipe.md)
-//   64 < Np <= 128, DENSE call, >= 2 items per SM            : attention_pipe.cu, one-tile items: whole rows per thread, the two exp
-//                                    warps of a scheduler on alternate tiles (1.3-1.5x the kernel below: 87 tokens 43.5 -> 30.8 us)
-//   other Np <= 256                : attention_tc.cu    (two score tiles of 256 columns; the faster one for gathered calls of
-//                                    <= 128 keys - 7 loader warps against 3 -, for <= 64 tokens - it packs several images into a
-//                                    tile - and for launches of a few items per SM).  The two agree bit for bit.
+//   128 < Np, Np_pad <= 224        : attention_pipe.cu  (role-pipelined: exp / epilogue / MMA / load warps, S multi-buffered in
+//                                    TMEM, half rows of S held in registers): 1.2-1.26x the kernel below at 152..197 tokens and
+//                                    batch 256, 1.35-1.5x at 16..64 images, dense or gathered; never slower down to 4 images
+//   64 < Np <= 128, dense, >= 1 (image, head) item per SM,
+//                or gathered, <= 4 items per SM : attention_pipe.cu, one-tile items: whole rows per thread, the two exp warps of
+//                                    a scheduler on alternate tiles (dense 87 tokens at batch 256: 43.5 -> 30.8 us; gathered calls
+//                                    of the 32..64-image shards 1.05-1.2x; at 20 items per SM the gathered load is the bound and
+//                                    the kernel below, with 7 loader warps against 3, wins by 3-8 %)
+//   other Np <= 256                : attention_tc.cu    (two score tiles of 256 columns at once; <= 64 tokens - it packs several
+//                                    images into a tile -, large gathered one-tile launches, Np_pad > 224).  The two agree bit
+//                                    for bit.  (profiles/r2_attention_pipe.md, r2_attention_fullrow_ab.txt)
 //   else                           : attention_long.cu  (key blocks of 224, two passes; the 577-token configuration)
 //
 // RAJNI_ATTN_TC=1 sends every Np <= 256 call to attention_tc.cu, RAJNI_ATTN_PIPE=1 every Np_pad <= 224 call to
@@ -39,9 +42,10 @@ static int attention_dispatch(const void* qkv, const int32_t* row_map, void* out
         const int np_pad = (Np + 15) & ~15;
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, current_device());
-        const bool big = Np > 128 && (long long)B * H >= 6LL * sms;
-        const bool one_tile_dense = Np > 64 && Np <= 128 && row_map == nullptr && (long long)B * H >= 2LL * sms;
-        if (np_pad <= 224 && (force_pipe || (!force_tc && (big || one_tile_dense)))) impl = RAJNI_ATTN_PIPE;
+        const long long items = (long long)B * H;
+        const bool big = Np > 128;
+        const bool one_tile = Np > 64 && Np <= 128 && (row_map == nullptr ? items >= sms : items <= 4LL * sms);
+        if (np_pad <= 224 && (force_pipe || (!force_tc && (big || one_tile)))) impl = RAJNI_ATTN_PIPE;
         else impl = Np <= 256 ? RAJNI_ATTN_TC : RAJNI_ATTN_LONG;
     }
     int rc = 0;

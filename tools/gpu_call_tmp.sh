@@ -1,3 +1,3 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2g_bench_2gpu.json 2> gpurun_out/r2g_bench_2gpu.err; echo "rc=$?"
-tail -c 300 gpurun_out/r2g_bench_2gpu.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/r2g_bench_ref_2gpu.json 2> gpurun_out/r2g_bench_ref_2gpu.err; echo "ref rc=$?"
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2h_tests.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/r2h_tests.log
+timeout 300 python tools/c2_small_batch_probe.py > gpurun_out/small_batch_pipe2.log 2>&1; cat gpurun_out/small_batch_pipe2.log
+timeout 600 python tools/config_profile.py C3/8 C4/8 > gpurun_out/config_profile_shard2.txt 2>&1; grep -E "bs|attention" gpurun_out/config_profile_shard2.txt
