@@ -1,2 +1,3 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 50 --warmup 5 > gpurun_out/r2i_bench_8gpu.json 2> gpurun_out/r2i_bench_8gpu.err; echo "rc=$?"
-tail -c 300 gpurun_out/r2i_bench_8gpu.err
+timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -k "score or select or importance" > gpurun_out/fs_tests.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/fs_tests.log
+timeout 300 python tools/score_small_bench.py > gpurun_out/score_small_fused.txt 2>&1; cat gpurun_out/score_small_fused.txt
+RAJNI_SCORE_TWO_LAUNCHES=1 timeout 300 python tools/score_small_bench.py > gpurun_out/score_small_two.txt 2>&1; cat gpurun_out/score_small_two.txt
