@@ -98,7 +98,9 @@ def select(scores: torch.Tensor, keep: int, keep_idx=None, next_scores=None, row
     return keep_idx, next_scores, row_map
 
 
-SPLIT_SCORE_MAX_BATCH = 96      # below this many images per launch the K/V pass is spread over (image, row-block) CTAs
+# Up to this many images per launch (about one per SM) the K/V pass is spread over (image, row-block) CTAs: at 197 tokens the
+# split path wins up to ~160 images (128: 27.8 vs 30.9 us), at 577 tokens by 12 % at 128 (profiles/r2_score_select.md)
+SPLIT_SCORE_MAX_BATCH = 148
 _score_ws = {}
 
 

@@ -29,8 +29,11 @@ def timeit(fn, inner=50, iters=7):
     return sorted(ts)[len(ts) // 2] * 1e3
 
 
-for name, B, N, H, r in (("C3 vit_small bs64", 64, 197, 6, 0.7), ("C3 late layer", 64, 60, 6, 0.7), ("C4 vit_large bs32", 32, 197, 16, 0.9),
-                         ("C4 late layer", 32, 40, 16, 0.9), ("C5 deit384 bs16", 16, 577, 12, 0.88), ("C2 bs256", 256, 197, 12, 0.88)):
+CASES = (("C3 vit_small bs64", 64, 197, 6, 0.7), ("C3 late layer", 64, 60, 6, 0.7), ("C4 vit_large bs32", 32, 197, 16, 0.9),
+                         ("C4 late layer", 32, 40, 16, 0.9), ("C5 deit384 bs16", 16, 577, 12, 0.88), ("C2 bs256", 256, 197, 12, 0.88))
+if len(sys.argv) > 1:        # score_small_bench.py B:N:H ...   (other shapes)
+    CASES = tuple((a, *[int(v) for v in a.split(":")], 0.88) for a in sys.argv[1:])
+for name, B, N, H, r in CASES:
     keep = max(1, int(r * (N - 1)))
     nbuf = max(1, min(4, int(400e6 // (B * N * 3 * H * 64 * 2)) + 1))     # rotate over > 126 MB of inputs: the pass comes from HBM
     qkvs = [torch.randn(B, N, 3 * H * 64, device="cuda").bfloat16() for _ in range(nbuf)]
