@@ -171,11 +171,17 @@ def test_evaluate_model_data_parallel_gloo(tmp_path):
     """the batch is sharded contiguously by rank and the only collective is the final reduction of
     (correct, total, images) and MAX(time); a 2-rank run must report the single-process accuracy exactly."""
     acc1, _ = evaluate_model(_StubModel(), _make_data(), device="cpu", warmup=1, progress=False)
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
     out = str(tmp_path / "dp.json")
-    mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+    for attempt in range(2):                     # (a free port can be taken between the probe and the rendezvous: one retry)
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        try:
+            mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+            break
+        except Exception:
+            if attempt:
+                raise
     got = json.load(open(out))
     assert got["acc"] == pytest.approx(acc1, abs=1e-9)
     assert got["ips"] > 0
