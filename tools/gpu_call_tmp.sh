@@ -1,1 +1,5 @@
-timeout 300 python tools/score_small_bench.py 96:197:12 128:197:12 160:197:12 192:197:12 128:577:12 64:577:12 128:446:12 128:257:12 256:100:16 256:60:16 512:138:6 512:67:6 > gpurun_out/score_split_threshold.txt 2>&1; cat gpurun_out/score_split_threshold.txt
+python -m pytest tests -m gpu -x -q > gpurun_out/r2j_tests.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/r2j_tests.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2j_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/r2j_smoke.log
+python bench.py > gpurun_out/r2j_bench.json 2> gpurun_out/r2j_bench.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2j_bench_ref.json 2> gpurun_out/r2j_bench_ref.err; echo "ref rc=$?"
+timeout 600 python tools/config_profile.py C3/4 C4/2 C5 > gpurun_out/config_profile_mid.txt 2>&1; grep -E "bs|score_select" gpurun_out/config_profile_mid.txt
