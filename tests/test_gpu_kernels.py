@@ -397,7 +397,10 @@ def test_select_nan_sorts_largest(ops):
                                       (2, 152, 121, 12), (2, 121, 87, 12), (1, 577, 507, 12), (2, 577, 577, 3), (1, 507, 446, 12), (3, 357, 257, 6), (2, 300, 300, 2), (1, 1000, 700, 2), (2, 64, 64, 1),
                                       (2, 65, 65, 1), (2, 197, 2, 3), (2, 250, 250, 2), (1, 300, 240, 3), (2, 256, 256, 1), (3, 130, 129, 2), (2, 192, 192, 2), (2, 200, 193, 2),
                                       # short images packed k to a tile (k divides B, k * Np <= 128): k = 8, 3, 4, 5, 2, and 3 images that cannot pack
-                                      (16, 20, 14, 2), (6, 33, 33, 3), (4, 50, 23, 4), (5, 16, 16, 1), (10, 70, 58, 2), (3, 64, 64, 2), (8, 12, 11, 6)])
+                                      (16, 20, 14, 2), (6, 33, 33, 3), (4, 50, 23, 4), (5, 16, 16, 1), (10, 70, 58, 2), (3, 64, 64, 2), (8, 12, 11, 6),
+                                      # several items per CTA (> 148 items): the second tile's rows rotate over the lane quadrants (24, 45, 64 live
+                                      # rows), one-tile items alternate between the two exp-warp sets
+                                      (40, 173, 152, 12), (36, 197, 173, 12), (60, 192, 192, 6), (40, 130, 129, 12), (50, 87, 87, 12), (48, 121, 87, 12)])
 def test_attention(ops, B, N, Np, H):
     """Every kernel that covers the shape (include/rajni_b200.h: RAJNI_ATTN_*), not only the one the dispatcher picks."""
     from rajni_vit_b200 import _lib

@@ -1,5 +1,5 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/r2j_tests.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/r2j_tests.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2j_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/r2j_smoke.log
-python bench.py > gpurun_out/r2j_bench.json 2> gpurun_out/r2j_bench.err; echo "bench rc=$?"
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2j_bench_ref.json 2> gpurun_out/r2j_bench_ref.err; echo "ref rc=$?"
-timeout 600 python tools/config_profile.py C3/4 C4/2 C5 > gpurun_out/config_profile_mid.txt 2>&1; grep -E "bs|score_select" gpurun_out/config_profile_mid.txt
+timeout 900 python -m pytest tests/test_gpu_kernels.py -x -q -k "attention" > gpurun_out/rot_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/rot_tests.log
+timeout 300 python tools/attn_ab.py 152:152 173:152 173:173 197:173 138:138 159:143 > gpurun_out/attn_ab_rot3.txt 2>&1; cat gpurun_out/attn_ab_rot3.txt
+RAJNI_ATTN_ROT=1 timeout 300 python tools/attn_ab.py 152:152 173:152 173:173 197:173 138:138 159:143 > gpurun_out/attn_ab_rot1.txt 2>&1; cat gpurun_out/attn_ab_rot1.txt
+RAJNI_ATTN_ROT=4 timeout 300 python tools/attn_ab.py 152:152 173:152 138:138 > gpurun_out/attn_ab_rot4.txt 2>&1; cat gpurun_out/attn_ab_rot4.txt
+RAJNI_ATTN_ROT=2 timeout 300 python tools/attn_ab.py 152:152 173:152 173:173 197:197 > gpurun_out/attn_ab_rot2.txt 2>&1; cat gpurun_out/attn_ab_rot2.txt
