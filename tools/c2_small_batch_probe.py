@@ -4,7 +4,7 @@ from rajni_vit_b200 import RAJNIViTWrapper, ops
 from rajni_vit_b200.vit import create_model
 S = {3: {"keep_ratio": 0.88}, 4: {"keep_ratio": 0.88}, 7: {"keep_ratio": 0.8}, 8: {"keep_ratio": 0.72}}
 m = RAJNIViTWrapper(create_model("vit_base_patch16_224", seed=0), S).cuda().eval()
-for B in (32, 64):
+for B in ([int(v) for v in sys.argv[1:]] or [32, 64]):
     x = torch.randn(B, 3, 224, 224, device="cuda")
     for mode in (False, None):
         m.use_cuda_graph = mode
