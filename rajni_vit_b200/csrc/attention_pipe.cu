@@ -56,7 +56,7 @@ constexpr int kApSumSlots = 8;
 constexpr int kApPolyEvery = AP_POLY_EVERY;               // one exponential in this many is a polynomial on the FMA pipe (0: all on MUFU)
 constexpr int kApOutStage = 4 * 4096;                                          // 32 rows x 128 B per helper warp
 constexpr int kApAuxBytes = 2 * 2 * 128 * 4 + kApSumSlots * 2 * 128 * 4;       // half-row maxima (2 parities), partial row sums
-constexpr int kApBarBytes = 256;
+constexpr int kApBarBytes = 320;
 constexpr int kApSmemBudget = 227 * 1024 - 1024 - kApOutStage - kApAuxBytes - kApBarBytes;
 
 #ifdef RAJNI_ATTN_TRACE
@@ -280,13 +280,15 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
     uint64_t* bars = reinterpret_cast<uint64_t*>(sums + kApSumSlots * 2 * 128);
     uint64_t* qk_full = bars;                        // [4] loader -> MMA
     uint64_t* v_full = bars + 4;                     // [4] loader -> MMA
-    uint64_t* stage_empty = bars + 8;                // [4] MMA -> loader (tcgen05.commit after the item's last P V)
+    uint64_t* stage_empty = bars + 8;                // [4] MMA -> loader (tcgen05.commit after the item's last P V): the V plane is free
     uint64_t* s_full = bars + 12;                    // [4 bufs] MMA -> exp warps (S ready)
     uint64_t* s_taken = bars + 16;                   // [4 bufs] exp warps -> MMA (S is in registers: the tensor pipe may start P V)
     uint64_t* p_full = bars + 20;                    // [4 bufs] exp warps -> MMA (P in TMEM)
     uint64_t* o_full = bars + 24;                    // [2] MMA -> helpers
     uint64_t* o_empty = bars + 26;                   // [2] helpers -> MMA (O read out)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+    uint64_t* qk_empty = bars + 28;                  // [4] MMA -> loader (commit after the item's last S): the Q and K planes are free -
+                                                     //     a tile time or two before the V plane, and Q/K are 2/3 of the next item's bytes
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -298,6 +300,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
                 mbar_init(&qk_full[i], p.row_map ? kApLoaderThreads : 1);
                 mbar_init(&v_full[i], p.row_map ? kApLoaderThreads : 1);
                 mbar_init(&stage_empty[i], 1);
+                mbar_init(&qk_empty[i], 1);
             }
             for (int i = 0; i < kApMaxBufs; ++i) {
                 mbar_init(&s_full[i], 1);
@@ -335,12 +338,13 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
             for (int n = 0; n < n_mine; ++n) {
                 const int item = ap_item(p, n);
                 const int b = item / p.H, h = item - b * p.H;
-                mbar_wait(&stage_empty[stage], phase ^ 1);
-                mbar_expect_tx(&qk_full[stage], 2u * plane_tx);
-                mbar_expect_tx(&v_full[stage], plane_tx);
                 uint8_t* sq = smem_gen + stage * stage_bytes;
+                mbar_wait(&qk_empty[stage], phase ^ 1);
+                mbar_expect_tx(&qk_full[stage], 2u * plane_tx);
                 tma_load_3d(sq, &tmap_qkv, &qk_full[stage], h * 64, 0, b);
                 tma_load_3d(sq + p.plane_bytes, &tmap_qkv, &qk_full[stage], p.C + h * 64, 0, b);
+                mbar_wait(&stage_empty[stage], phase ^ 1);
+                mbar_expect_tx(&v_full[stage], plane_tx);
                 tma_load_3d(sq + 2 * p.plane_bytes, &tmap_qkv, &v_full[stage], 2 * p.C + h * 64, 0, b);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
@@ -362,11 +366,11 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
                 const int j = grp + i * kApLoaderGroups;
                 grow[i] = j < Np ? __ldg(p.row_map + (long long)b * Np + j) : -1;
             }
-            mbar_wait(&stage_empty[stage], phase ^ 1);
             const uint32_t sq = smem_base + stage * stage_bytes, sk = sq + p.plane_bytes, sv = sk + p.plane_bytes;
             const __nv_bfloat16* base = p.qkv + h * 64 + chunk * 8;
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {                    // pass 0: Q and K (what S needs), pass 1: V
+                mbar_wait(pass == 0 ? &qk_empty[stage] : &stage_empty[stage], phase ^ 1);
 #pragma unroll
                 for (int i = 0; i < kApSweeps; ++i) {
                     const int j = grp + i * kApLoaderGroups;
@@ -416,6 +420,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
                 for (int k = 0; k < 4; ++k)
                     umma_bf16(d, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_s, k != 0);
                 umma_commit(&s_full[s.buf]);
+                if (s.j == p.tpi - 1) umma_commit(&qk_empty[s.stage]);         // the item's last S: its Q and K planes may be refilled
                 AP_TRACE(s.g, 1);
                 s.advance(p);
             };
